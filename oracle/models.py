@@ -1,0 +1,140 @@
+"""TEST INFRASTRUCTURE — CPU oracle, model definitions.  Not part of the product path.
+
+Independent sympy restatement of the reference's JinEnv models and of the time-warping wrapper every
+example puts around them (dyn = beta*f, path = beta*c, final = h unscaled).  Written straight from the
+reference formulas, NOT through the product's ``lfsd_b200.sx`` / ``lfsd_b200.JinEnv`` layer, so that
+``tests/test_models.py`` can cross-check the two derivations numerically.
+
+Follows:
+  * SinglePendulum  /root/reference/JinEnv/JinEnv.py:44-107
+  * RobotArm        /root/reference/JinEnv/JinEnv.py:183-237, 287-326
+  * Quadrotor       /root/reference/JinEnv/JinEnv.py:680-753, 886-953, 1182-1205
+  * Rocket          /root/reference/JinEnv/JinEnv.py:1266-1326, 1401-1473
+  * beta wrapper    /root/reference/Examples/pendulum_groundtruth.py:21-30 (same in every example,
+                    /root/reference/lib/QuadAlgorithm.py:89-98)
+"""
+import math
+
+import numpy as np
+import sympy as sp
+
+
+class OracleModel:
+    """x (n), u (m), theta (r) symbols and the three expressions dyn (n), path (scalar), final (scalar).
+    ``sel`` lists the state indices observed by the loss closure of the matching example."""
+
+    def __init__(self, name, x, u, theta, dyn, path, final, sel):
+        self.name = name
+        self.x, self.u, self.theta = list(x), list(u), list(theta)
+        self.n, self.m, self.r = len(self.x), len(self.u), len(self.theta)
+        self.dyn = sp.Matrix(dyn)
+        self.path = sp.sympify(path)
+        self.final = sp.sympify(final)
+        self.sel = list(sel)
+
+
+def _syms(names):
+    return [sp.Symbol(s, real=True) for s in names.split()]
+
+
+def _dcm(q):
+    q0, q1, q2, q3 = q
+    return sp.Matrix([
+        [1 - 2 * (q2 ** 2 + q3 ** 2), 2 * (q1 * q2 + q0 * q3), 2 * (q1 * q3 - q0 * q2)],
+        [2 * (q1 * q2 - q0 * q3), 1 - 2 * (q1 ** 2 + q3 ** 2), 2 * (q2 * q3 + q0 * q1)],
+        [2 * (q1 * q3 + q0 * q2), 2 * (q2 * q3 - q0 * q1), 1 - 2 * (q1 ** 2 + q2 ** 2)]])
+
+
+def _quat_rate(q, w):
+    wx, wy, wz = w
+    Om = sp.Matrix([[0, -wx, -wy, -wz], [wx, 0, wz, -wy], [wy, -wz, 0, wx], [wz, wy, -wx, 0]])
+    return Om * sp.Matrix(q) / 2
+
+
+def _euler(J, M, w):
+    Jm = sp.diag(*J)
+    wv = sp.Matrix(w)
+    return Jm.inv() * (sp.Matrix(M) - wv.cross(Jm * wv))
+
+
+def pendulum(l=1.0, m=1.0, damping=0.1, wu=0.01):
+    q, dq = _syms('q dq')
+    u, = _syms('u')
+    beta, wq, wdq = _syms('beta wq wdq')
+    g = 10
+    inertia = sp.Rational(1, 3) * m * l * l
+    f = sp.Matrix([dq, (u - m * g * l * sp.sin(q) - damping * dq) / inertia])
+    h = wq * (q - math.pi) ** 2 + wdq * dq ** 2
+    c = h + wu * u ** 2
+    return OracleModel('pendulum', [q, dq], [u], [beta, wq, wdq], beta * f, beta * c, h, sel=[0])
+
+
+def robotarm(l1=1.0, m1=1.0, l2=1.0, m2=1.0, g=0.0, wu=0.5):
+    q1, q2, dq1, dq2 = _syms('q1 q2 dq1 dq2')
+    u1, u2 = _syms('u1 u2')
+    beta, w1s, w1, w2s, w2 = _syms('beta w_q1_sq w_q1 w_q2_sq w_q2')
+    r1, r2 = l1 / 2, l2 / 2
+    I1, I2 = l1 * l1 * m1 / 12, l2 * l2 * m2 / 12
+    M11 = m1 * r1 * r1 + I1 + m2 * (l1 * l1 + r2 * r2 + 2 * l1 * r2 * sp.cos(q2)) + I2
+    M12 = m2 * (r2 * r2 + l1 * r2 * sp.cos(q2)) + I2
+    M22 = m2 * r2 * r2 + I2
+    Mm = sp.Matrix([[M11, M12], [M12, M22]])
+    hh = m2 * l1 * r2 * sp.sin(q2)
+    C = sp.Matrix([-hh * dq2 * dq2 - 2 * hh * dq1 * dq2, hh * dq1 * dq1])
+    G = sp.Matrix([m1 * r1 * g * sp.cos(q1) + m2 * g * (r2 * sp.cos(q1 + q2) + l1 * sp.cos(q1)),
+                   m2 * g * r2 * sp.cos(q1 + q2)])
+    det = M11 * M22 - M12 * M12
+    Minv = sp.Matrix([[M22, -M12], [-M12, M11]]) / det
+    ddq = Minv * (-C - G + sp.Matrix([u1, u2]))
+    f = sp.Matrix([dq1, dq2, ddq[0], ddq[1]])
+    c = w1 * q1 + w1s * q1 * q1 / 2 + w2 * q2 + w2s * q2 * q2 / 2 + wu * (u1 ** 2 + u2 ** 2)
+    h = 100 * ((q1 - math.pi / 2) ** 2 + q2 ** 2 + dq1 ** 2 + dq2 ** 2)
+    return OracleModel('robotarm', [q1, q2, dq1, dq2], [u1, u2], [beta, w1s, w1, w2s, w2],
+                       beta * f, beta * c, h, sel=[0, 1])
+
+
+def quadrotor(goal_r=(0., 0., 0.), goal_v=(0., 0., 0.), goal_q=(1., 0., 0., 0.), goal_w=(0., 0., 0.),
+              J=(1.0, 1.0, 1.0), mass=1.0, l=1.0, c=0.02, w_thrust=0.1):
+    r = _syms('rx ry rz'); v = _syms('vx vy vz'); q = _syms('q0 q1 q2 q3'); w = _syms('wx wy wz')
+    f_ = _syms('f1 f2 f3 f4')
+    beta, wxs, wx_, wys, wy_, wzs, wz_ = _syms('beta w_xsq w_x w_ysq w_y w_zsq w_z')
+    thrust = sp.Matrix([0, 0, sum(f_)])
+    Mb = [(-f_[1] + f_[3]) * l / 2, (-f_[0] + f_[2]) * l / 2, (f_[0] - f_[1] + f_[2] - f_[3]) * c]
+    C_I_B = _dcm(q).T
+    dv = C_I_B * thrust / mass + sp.Matrix([0, 0, -9.81])
+    f = sp.Matrix([*v, *dv, *_quat_rate(q, w), *_euler(J, Mb, w)])
+    path = (wxs * r[0] ** 2 / 2 + wx_ * r[0] + wys * r[1] ** 2 / 2 + wy_ * r[1] + wzs * r[2] ** 2 / 2 + wz_ * r[2]
+            + w_thrust * sum(fi ** 2 for fi in f_))
+    att = (sp.eye(3) - _dcm(goal_q).T * _dcm(q)).trace()
+    h = (1 * sum((a - b) ** 2 for a, b in zip(r, goal_r)) + 11 * sum((a - b) ** 2 for a, b in zip(v, goal_v))
+         + 100 * att + 10 * sum((a - b) ** 2 for a, b in zip(w, goal_w)))
+    return OracleModel('quadrotor', r + v + q + w, f_, [beta, wxs, wx_, wys, wy_, wzs, wz_],
+                       beta * f, beta * path, h, sel=[0, 1, 2])
+
+
+def rocket(J=(1.0, 1.0, 1.0), mass=1.0, l=1.0, wthrust=0.1):
+    r = _syms('rx ry rz'); v = _syms('vx vy vz'); q = _syms('q0 q1 q2 q3'); w = _syms('wx wy wz')
+    u = _syms('ux uy uz')
+    names = 'wrx wry wrz wvx wvy wvz wwx wwy wwz wsidethrust wtilt'
+    beta, = _syms('beta')
+    wts = _syms(names)
+    wr, wv, ww, wside, wtilt = wts[0:3], wts[3:6], wts[6:9], wts[9], wts[10]
+    C_I_B = _dcm(q).T
+    T_B = sp.Matrix(u)
+    dv = C_I_B * T_B / mass + sp.Matrix([-10, 0, 0])
+    r_T = sp.Matrix([-l / 2, 0, 0])
+    f = sp.Matrix([*v, *dv, *_quat_rate(q, w), *_euler(J, r_T.cross(T_B), w)])
+    bx = C_I_B * sp.Matrix([1, 0, 0])
+    tilt = bx[1] ** 2 + bx[2] ** 2
+    h = (sum(a * b ** 2 for a, b in zip(wr, r)) + sum(a * b ** 2 for a, b in zip(wv, v))
+         + sum(a * b ** 2 for a, b in zip(ww, w)) + wtilt * tilt)
+    c = h + wside * (u[1] ** 2 + u[2] ** 2) + wthrust * sum(ui ** 2 for ui in u)
+    return OracleModel('rocket', r + v + q + w, u, [beta] + wts, beta * f, beta * c, h,
+                       sel=[0, 1, 2, 6, 7, 8, 9])
+
+
+def to_quaternion(angle, axis):
+    """/root/reference/JinEnv/JinEnv.py:1730-1737"""
+    d = np.asarray(axis, dtype=float)
+    d = d / np.linalg.norm(d)
+    return [math.cos(angle / 2)] + (math.sin(angle / 2) * d).tolist()
