@@ -1,0 +1,157 @@
+// Host-side orchestration behind the C ABI declared in include/cpdp.h.  Included by cpdp_lib.cu (nvcc, the shipped
+// library) and by tests/emu/emu_lib.cpp (g++, thread-per-CUDA-thread emulation used only by the CPU test-suite).
+// The includer provides:
+//   CPDP_LAUNCH(kernel, grid, block, smem_bytes, stream, ...)   launch
+//   CPDP_READ_INT(dst_host_int, src_dev_ptr, stream)            blocking read of one device int
+//   CPDP_NUM_SMS()                                              multiprocessor count
+//   CPDP_PREPARE_SMEM(kernel, bytes)                            opt in to > 48 KB dynamic shared memory
+//   CPDP_LAST_ERROR()                                           0 if no launch error
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace cpdp {
+
+struct WsLayout {
+    SolveArgs sa;
+    double* PW;
+    size_t bytes;
+};
+
+static inline size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// Carves the caller-provided workspace.  With base == nullptr only the size is computed.
+static WsLayout ws_carve(char* base, int B, int N, int S) {
+    WsLayout w;
+    size_t off = 0;
+    auto takeD = [&](size_t n) { double* p = base ? (double*)(base + off) : nullptr; off = al(off + n * sizeof(double)); return p; };
+    auto takeI = [&](size_t n) { int* p = base ? (int*)(base + off) : nullptr; off = al(off + n * sizeof(int)); return p; };
+    const size_t BN = (size_t)B * N, BN1 = (size_t)B * (N + 1);
+    SolveArgs& a = w.sa;
+    a.xs = takeD(BN * 4 * S * NX);
+    a.mu = takeD(BN * 4 * S * NX);
+    a.AB = takeD(BN * NX * NZ);
+    a.H = takeD(BN * NZ * NZ);
+    a.gL = takeD(BN * NZ);
+    a.dfc = takeD(BN1 * NX);
+    a.cost = takeD(BN);
+    a.Vs = takeD(BN1 * NX * NX);
+    a.vs = takeD(BN1 * NX);
+    a.Kf = takeD(BN * NU * NX);
+    a.kf = takeD(BN * NU);
+    a.gq = takeD(BN * NZ);
+    a.dX = takeD(BN1 * NX);
+    a.dU = takeD(BN * NU);
+    a.lamn = takeD(BN1 * NX);
+    a.nu = takeD(B);
+    a.dlast = takeD(B);
+    a.J = takeD(B);
+    a.kkt = takeD(B);
+    a.act = takeI(B);
+    a.nact = takeI(1);
+    w.PW = takeD(BN1 * NYR);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace cpdp
+
+extern "C" {
+
+int cpdp_model_dims(int* n, int* m, int* r) {
+    if (n) *n = cpdp::NX;
+    if (m) *m = cpdp::NU;
+    if (r) *r = cpdp::NP;
+    return 0;
+}
+
+int cpdp_riccati_state_dim(void) { return cpdp::NYR; }
+
+size_t cpdp_workspace_bytes(int B, int N, int S) {
+    if (B <= 0 || N <= 0 || S <= 0) return 0;
+    return cpdp::ws_carve(nullptr, B, N, S).bytes;
+}
+
+// Forward optimal-control solve for B problems (COCSys.cocSolver, CPDP.py:92-198).
+int cpdp_solve(void* ws, size_t ws_bytes, int B, int N, int S, double T,
+               const double* x0, const double* theta, int theta_stride,
+               double tol, int max_iter, int rounds,
+               double* X, double* U, double* Lam, int* status, int* iters,
+               double* kkt_out, double* cost_out, void* stream) {
+    using namespace cpdp;
+    if (!ws || B <= 0 || N <= 0 || S <= 0 || !x0 || !theta || !X || !U || !Lam || !status || !iters) return -1;
+    if (theta_stride != 0 && theta_stride != NP) return -2;
+    WsLayout w = ws_carve((char*)ws, B, N, S);
+    if (w.bytes > ws_bytes) return -3;
+    SolveArgs a = w.sa;
+    a.B = B; a.N = N; a.S = S; a.T = T; a.tol = tol; a.max_iter = max_iter;
+    a.x0 = x0; a.theta = theta; a.theta_stride = theta_stride;
+    a.X = X; a.U = U; a.Lam = Lam; a.status = status; a.iters = iters;
+    if (kkt_out) a.kkt = kkt_out;
+    if (cost_out) a.J = cost_out;
+    const int sms = CPDP_NUM_SMS();
+    cudaStream_t st = (cudaStream_t)stream;
+    CPDP_LAUNCH(k_solve_init, sms * 4, 256, 0, st, a);
+    CPDP_LAUNCH(k_compact, 1, COMPACT_THREADS, 0, st, a);
+    const int total_rounds = (rounds > 0) ? rounds : max_iter + 1;
+    for (int it = 0; it < total_rounds; ++it) {
+        CPDP_LAUNCH(k_stage_adjoint, sms * 8, 128, 0, st, a);
+        CPDP_LAUNCH(k_stage_hessian, sms * 4, HESS_THREADS, 0, st, a);
+        CPDP_LAUNCH(k_newton_step, sms * 16, NEWTON_THREADS, 0, st, a);
+        CPDP_LAUNCH(k_compact, 1, COMPACT_THREADS, 0, st, a);
+        if (rounds <= 0 && it >= 3) {     // adaptive mode: poll the active count (host sync)
+            int nact = 0;
+            CPDP_READ_INT(nact, a.nact, st);
+            if (nact == 0) break;
+        }
+    }
+    return CPDP_LAST_ERROR();
+}
+
+// Auxiliary system + loss (COCSys.auxSysSolver, CPDP.py:301-381; loss closures QuadAlgorithm.py:616-639).
+// mode 0: backward Riccati sweep with RK45 (rtol_b, atol_b); mode 1: BDF emulation of the as-shipped reference.
+int cpdp_aux(void* ws, size_t ws_bytes, int B, int N, int S, double T,
+             const double* theta, int theta_stride,
+             const double* X, const double* U, const double* Lam, const int* solve_status,
+             int mode, double rtol_b, double atol_b, double rtol_f, double atol_f,
+             int W, int D, const int* sel_host, const double* taus, int taus_stride, const double* wp,
+             double* Xa, double* Ua, double* loss, double* dtheta, int* aux_status, int* counters, void* stream) {
+    using namespace cpdp;
+    if (!ws || B <= 0 || N <= 0 || !theta || !X || !U || !Lam || !Xa || !Ua || !loss || !dtheta || !aux_status || !counters) return -1;
+    if (theta_stride != 0 && theta_stride != NP) return -2;
+    if (W < 0 || D < 0 || D > MAX_SEL || (W > 0 && (!taus || !wp || !sel_host))) return -4;
+    if (W > 0 && taus_stride != 0 && taus_stride != W) return -5;
+    WsLayout w = ws_carve((char*)ws, B, N, S);
+    if (w.bytes > ws_bytes) return -3;
+    AuxArgs a;
+    a.B = B; a.N = N; a.T = T; a.theta = theta; a.theta_stride = theta_stride;
+    a.X = X; a.U = U; a.Lam = Lam;
+    a.rtol_b = rtol_b; a.atol_b = atol_b; a.rtol_f = rtol_f; a.atol_f = atol_f;
+    a.PW = w.PW; a.Xa = Xa; a.Ua = Ua;
+    a.W = W; a.D = D;
+    for (int i = 0; i < MAX_SEL; ++i) a.sel[i] = (i < D) ? sel_host[i] : 0;
+    for (int i = 0; i < D; ++i) if (a.sel[i] < 0 || a.sel[i] >= NX) return -6;
+    a.taus = taus; a.taus_stride = taus_stride; a.wp = wp;
+    a.loss = loss; a.dtheta = dtheta; a.solve_status = solve_status; a.aux_status = aux_status; a.counters = counters;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ric_bytes = RIC_SMEM_DOUBLES * sizeof(double), fwd_bytes = FWD_SMEM_DOUBLES * sizeof(double);
+    if (mode == 0) {
+        CPDP_PREPARE_SMEM(k_riccati_rk45, ric_bytes);
+        CPDP_LAUNCH(k_riccati_rk45, B, AUX_THREADS, ric_bytes, st, a);
+    } else {
+        return -7;
+    }
+    CPDP_PREPARE_SMEM(k_aux_forward, fwd_bytes);
+    CPDP_LAUNCH(k_aux_forward, B, AUX_THREADS, fwd_bytes, st, a);
+    return CPDP_LAST_ERROR();
+}
+
+// Fixed-shape binary-tree sum over B rows of [loss | dL/dtheta] -> out[1+NP].  scratch: nextpow2(B)*(1+NP) doubles.
+int cpdp_reduce(const double* loss, const double* dtheta, int B, double* scratch, double* out, void* stream) {
+    using namespace cpdp;
+    if (!loss || !dtheta || !out || !scratch || B <= 0) return -1;
+    CPDP_LAUNCH(k_reduce_tree, 1, 256, 0, (cudaStream_t)stream, loss, dtheta, B, scratch, out);
+    return CPDP_LAST_ERROR();
+}
+
+}  // extern "C"

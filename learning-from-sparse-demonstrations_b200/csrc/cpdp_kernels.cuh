@@ -1,0 +1,622 @@
+// CPDP gradient-iteration kernels (fp64, sm_100a).  Included AFTER a generated model header that defines
+// `struct Model` (see codegen.py).  One shared library is built per model.
+//
+// Path and reference mapping:
+//   forward solve  : k_stage_adjoint + k_stage_hessian + k_newton_step   <- COCSys.cocSolver   CPDP.py:92-198
+//   Riccati sweep  : k_riccati_rk45 / k_riccati_bdf                      <- auxSysSolver       CPDP.py:316-338
+//   forward sweep  : k_aux_forward (+ fused loss / dL/dtheta)            <- auxSysSolver       CPDP.py:341-381
+//                                                                           loss closures QuadAlgorithm.py:616-639
+//   reduction      : k_reduce_tree                                        (new: cross-problem sum, fixed order)
+// No tensor cores: per-step matrices are <= 13x13 (+ sparse), fp64.  Bound: FP64 pipe / latency, not HBM.
+#pragma once
+#include "cpdp_port.h"
+
+namespace cpdp {
+
+constexpr int NX = Model::NX;
+constexpr int NU = Model::NU;
+constexpr int NP = Model::NP;
+constexpr int NZ = NX + NU;
+
+enum Status { ST_RUNNING = 0, ST_CONVERGED = 1, ST_MAXITER = 2, ST_LINESEARCH = 3, ST_NUMERIC = 4 };
+
+// ------------------------------------------------------------------------------------------------
+// Arguments of the forward-solve kernels (passed by value).
+// ------------------------------------------------------------------------------------------------
+struct SolveArgs {
+    int B, N, S;                 // problems, grid intervals, RK4 substeps per interval
+    double T;                    // horizon
+    double tol;                  // KKT tolerance
+    int max_iter;
+    const double* x0;            // [B][NX]
+    const double* theta;         // [B or 1][NP]
+    int theta_stride;            // NP or 0
+    double* X;                   // [B][N+1][NX]   NLP states (in/out)
+    double* U;                   // [B][N+1][NU]   NLP controls, row N := row N-1 on exit
+    double* Lam;                 // [B][N+1][NX]   multipliers of [x0-X0, F_k-X_{k+1}]
+    int* status;                 // [B]
+    int* iters;                  // [B]
+    // workspace
+    double* xs;                  // [B*N][4S][NX]  RK4 stage states
+    double* mu;                  // [B*N][4S][NX]  stage adjoints
+    double* AB;                  // [B*N][NX][NZ]  dF/d(x,u)
+    double* H;                   // [B*N][NZ][NZ]  Hess (q + lam'F)
+    double* gL;                  // [B*N][NZ]      grad (q + lam'F)
+    double* dfc;                 // [B][N+1][NX]   defects (row 0 unused here)
+    double* cost;                // [B*N]
+    double* Vs;                  // [B][N+1][NX*NX]
+    double* vs;                  // [B][N+1][NX]
+    double* Kf;                  // [B*N][NU][NX]
+    double* kf;                  // [B*N][NU]
+    double* gq;                  // [B*N][NZ]
+    double* dX;                  // [B][N+1][NX]
+    double* dU;                  // [B][N][NU]
+    double* lamn;                // [B][N+1][NX]
+    double* nu;                  // [B]  merit penalty
+    double* dlast;               // [B]  last inertia-correction delta
+    double* J;                   // [B]  objective at the current iterate
+    double* kkt;                 // [B]  KKT error at the current iterate
+    int* act;                    // [B]  compacted list of problems still iterating
+    int* nact;                   // [1]
+};
+
+CPDP_HD const double* theta_of(const SolveArgs& a, int b) { return a.theta + (size_t)b * a.theta_stride; }
+
+// One classical RK4 step of (f, c) with frozen control (CPDP.py:117-123).
+CPDP_HD void rk4_step(const double* x, const double* u, const double* th, double DT, double* xn, double& q) {
+    double k[NX], xt[NX], c;
+    Model::fc(x, u, th, k, c);
+    double qa = c;
+    for (int i = 0; i < NX; ++i) { xn[i] = x[i] + DT / 6 * k[i]; xt[i] = x[i] + DT / 2 * k[i]; }
+    Model::fc(xt, u, th, k, c);
+    qa += 2 * c;
+    for (int i = 0; i < NX; ++i) { xn[i] += DT / 3 * k[i]; xt[i] = x[i] + DT / 2 * k[i]; }
+    Model::fc(xt, u, th, k, c);
+    qa += 2 * c;
+    for (int i = 0; i < NX; ++i) { xn[i] += DT / 3 * k[i]; xt[i] = x[i] + DT * k[i]; }
+    Model::fc(xt, u, th, k, c);
+    qa += c;
+    for (int i = 0; i < NX; ++i) xn[i] += DT / 6 * k[i];
+    q += DT / 6 * qa;
+}
+
+// S RK4 steps over one grid interval: x -> x_end, q = integral of the path cost.
+CPDP_HD void rk4_interval(const double* x, const double* u, const double* th, double DT, int S, double* xe, double& q) {
+    double xa[NX], xb[NX];
+    for (int i = 0; i < NX; ++i) xa[i] = x[i];
+    q = 0.0;
+    for (int s = 0; s < S; ++s) {
+        rk4_step(xa, u, th, DT, xb, q);
+        for (int i = 0; i < NX; ++i) xa[i] = xb[i];
+    }
+    for (int i = 0; i < NX; ++i) xe[i] = xa[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_stage_adjoint: one thread per (problem, interval).
+// Forward RK4 rollout storing the 4S stage states, defect and cost; then the discrete adjoint of the interval map
+// seeded with lam_{k+1}, storing the 4S stage adjoints and grad_z (q_k + lam_{k+1}' F_k).
+// ------------------------------------------------------------------------------------------------
+CPDP_D void stage_adjoint_item(const SolveArgs& a, int b, int k);
+
+CPDP_GLOBAL void __launch_bounds__(128) k_stage_adjoint(SolveArgs a) {
+    const int total = *a.nact * a.N;
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x)
+        stage_adjoint_item(a, a.act[item / a.N], item % a.N);
+}
+
+CPDP_D void stage_adjoint_item(const SolveArgs& a, int b, int k) {
+    const int idx = b * a.N + k;
+    const double DT = a.T / a.N / a.S;
+    const double* th = theta_of(a, b);
+    double x[NX], u[NU];
+    {
+        const double* xk = a.X + ((size_t)b * (a.N + 1) + k) * NX;
+        const double* uk = a.U + ((size_t)b * (a.N + 1) + k) * NU;
+        for (int i = 0; i < NX; ++i) x[i] = xk[i];
+        for (int i = 0; i < NU; ++i) u[i] = uk[i];
+    }
+    double* xs = a.xs + (size_t)idx * 4 * a.S * NX;
+    double* mus = a.mu + (size_t)idx * 4 * a.S * NX;
+    double q = 0.0;
+    {   // forward
+        double kk[NX], xt[NX], xn[NX], c;
+        for (int s = 0; s < a.S; ++s) {
+            double* st = xs + (size_t)s * 4 * NX;
+            for (int i = 0; i < NX; ++i) st[i] = x[i];
+            Model::fc(x, u, th, kk, c);
+            double qa = c;
+            for (int i = 0; i < NX; ++i) { xn[i] = x[i] + DT / 6 * kk[i]; xt[i] = x[i] + DT / 2 * kk[i]; st[NX + i] = xt[i]; }
+            Model::fc(xt, u, th, kk, c);
+            qa += 2 * c;
+            for (int i = 0; i < NX; ++i) { xn[i] += DT / 3 * kk[i]; xt[i] = x[i] + DT / 2 * kk[i]; st[2 * NX + i] = xt[i]; }
+            Model::fc(xt, u, th, kk, c);
+            qa += 2 * c;
+            for (int i = 0; i < NX; ++i) { xn[i] += DT / 3 * kk[i]; xt[i] = x[i] + DT * kk[i]; st[3 * NX + i] = xt[i]; }
+            Model::fc(xt, u, th, kk, c);
+            qa += c;
+            for (int i = 0; i < NX; ++i) x[i] = xn[i] + DT / 6 * kk[i];
+            q += DT / 6 * qa;
+        }
+    }
+    {
+        const double* xn = a.X + ((size_t)b * (a.N + 1) + k + 1) * NX;
+        double* d = a.dfc + ((size_t)b * (a.N + 1) + k + 1) * NX;
+        for (int i = 0; i < NX; ++i) d[i] = x[i] - xn[i];
+        a.cost[idx] = q;
+    }
+    // backward (adjoint) sweep
+    double adj[NX], gu[NU];
+    {
+        const double* ln = a.Lam + ((size_t)b * (a.N + 1) + k + 1) * NX;
+        for (int i = 0; i < NX; ++i) adj[i] = ln[i];
+        for (int i = 0; i < NU; ++i) gu[i] = 0.0;
+    }
+    const double bco[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+    const double aco[4] = {0.0, 0.5, 0.5, 1.0};
+    for (int s = a.S - 1; s >= 0; --s) {
+        double ax[NX], xi[NX], kap[NX], g_u[NU], xst[NX];
+        for (int i = 0; i < NX; ++i) { ax[i] = 0.0; xi[i] = 0.0; }
+        for (int st = 3; st >= 0; --st) {
+            const double* xsp = xs + ((size_t)s * 4 + st) * NX;
+            for (int i = 0; i < NX; ++i) xst[i] = xsp[i];
+            const double cnext = (st < 3) ? aco[st + 1] * DT : 0.0;
+            for (int i = 0; i < NX; ++i) kap[i] = bco[st] * DT * adj[i] + cnext * xi[i];
+            double* mp = mus + ((size_t)s * 4 + st) * NX;
+            for (int i = 0; i < NX; ++i) mp[i] = kap[i];
+            Model::hgrad(xst, u, th, kap, bco[st] * DT, xi, g_u);
+            for (int i = 0; i < NX; ++i) ax[i] += xi[i];
+            for (int i = 0; i < NU; ++i) gu[i] += g_u[i];
+        }
+        for (int i = 0; i < NX; ++i) adj[i] += ax[i];
+    }
+    double* g = a.gL + (size_t)idx * NZ;
+    for (int i = 0; i < NX; ++i) g[i] = adj[i];
+    for (int i = 0; i < NU; ++i) g[NX + i] = gu[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_stage_hessian: NZ threads per (problem, interval), KPC intervals per CTA.
+// Thread j propagates column j of the forward sensitivity d(stage state)/d(x_k,u_k) through the 4S stages and
+// accumulates column j of  Hess = sum_s Sz_s' Hess_z(mu_s'f + w_s c) Sz_s ; writes [A B] and Hess.
+// ------------------------------------------------------------------------------------------------
+constexpr int HESS_THREADS = 256;
+constexpr int KPC = HESS_THREADS / NZ;          // intervals per CTA
+
+CPDP_GLOBAL void __launch_bounds__(HESS_THREADS) k_stage_hessian(SolveArgs a) {
+    CPDP_SHARED double s_x[KPC][NX];
+    CPDP_SHARED double s_mu[KPC][NX];
+    CPDP_SHARED double s_u[KPC][NU];
+    CPDP_SHARED double s_th[KPC][NP];
+    CPDP_SHARED double s_S[KPC][NZ][NX];
+    CPDP_SHARED int s_gi[KPC];                 // global interval index b*N+k of each slot, -1 if none
+    const int tid = threadIdx.x;
+    const int kk = tid / NZ, j = tid % NZ;
+    const int total = *a.nact * a.N;
+    const int ngroups = (total + KPC - 1) / KPC;
+    const double DT = a.T / a.N / a.S;
+    const double bco[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+    const double aco[4] = {0.0, 0.5, 0.5, 1.0};
+
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        __syncthreads();
+        for (int t = tid; t < KPC; t += HESS_THREADS) {
+            const int li = grp * KPC + t;
+            s_gi[t] = (li < total) ? a.act[li / a.N] * a.N + li % a.N : -1;
+        }
+        __syncthreads();
+        for (int t = tid; t < KPC * (NU + NP); t += HESS_THREADS) {
+            const int q = t / (NU + NP), e = t % (NU + NP);
+            const int gi = s_gi[q];
+            if (gi >= 0) {
+                const int b = gi / a.N, k = gi % a.N;
+                if (e < NU) s_u[q][e] = a.U[((size_t)b * (a.N + 1) + k) * NU + e];
+                else s_th[q][e - NU] = theta_of(a, b)[e - NU];
+            }
+        }
+        const bool mine = (kk < KPC) && (s_gi[kk < KPC ? kk : 0] >= 0);
+        const int gi = mine ? s_gi[kk] : -1;
+
+        double Sx[NX], Sn[NX], dX[NX], df[NX], du[NU], hz[NZ], Hc[NZ];
+        for (int i = 0; i < NX; ++i) { Sx[i] = (i == j) ? 1.0 : 0.0; df[i] = 0.0; }
+        for (int i = 0; i < NU; ++i) du[i] = (NX + i == j) ? 1.0 : 0.0;
+        for (int i = 0; i < NZ; ++i) Hc[i] = 0.0;
+
+        for (int s = 0; s < a.S; ++s) {
+            for (int i = 0; i < NX; ++i) Sn[i] = Sx[i];
+            for (int st = 0; st < 4; ++st) {
+                // stage state + adjoint for every interval of this group
+                for (int t = tid; t < KPC * 2 * NX; t += HESS_THREADS) {
+                    const int q = t / (2 * NX), e = t % (2 * NX);
+                    const int g2 = s_gi[q];
+                    if (g2 >= 0) {
+                        const size_t base = ((size_t)g2 * 4 * a.S + (size_t)s * 4 + st) * NX;
+                        if (e < NX) s_x[q][e] = a.xs[base + e];
+                        else s_mu[q][e - NX] = a.mu[base + e - NX];
+                    }
+                }
+                __syncthreads();
+                if (mine) {
+                    const double ca = aco[st] * DT;
+                    for (int i = 0; i < NX; ++i) dX[i] = Sx[i] + ca * df[i];
+                    Model::dir(s_x[kk], s_u[kk], s_th[kk], s_mu[kk], bco[st] * DT, dX, du, df, hz);
+                    for (int i = 0; i < NX; ++i) s_S[kk][j][i] = dX[i];
+                }
+                __syncthreads();
+                if (mine) {
+                    for (int i = 0; i < NZ; ++i) {
+                        double acc = (i >= NX) ? hz[i] : 0.0;
+                        const double* col = s_S[kk][i];
+                        for (int e = 0; e < NX; ++e) acc += col[e] * hz[e];
+                        Hc[i] += acc;
+                    }
+                    const double cb = bco[st] * DT;
+                    for (int i = 0; i < NX; ++i) Sn[i] += cb * df[i];
+                }
+            }
+            for (int i = 0; i < NX; ++i) Sx[i] = Sn[i];
+        }
+        if (mine) {
+            double* AB = a.AB + (size_t)gi * NX * NZ;
+            for (int i = 0; i < NX; ++i) AB[i * NZ + j] = Sx[i];
+            double* H = a.H + (size_t)gi * NZ * NZ;
+            for (int i = 0; i < NZ; ++i) H[i * NZ + j] = Hc[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small dense helpers used by one CTA (all threads call; results valid after the trailing barrier)
+// ------------------------------------------------------------------------------------------------
+CPDP_D double block_reduce(double v, double* red, bool is_max) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __syncthreads();
+    red[tid] = v;
+    __syncthreads();
+    if (tid == 0) {
+        double r = red[0];
+        for (int i = 1; i < nt; ++i) r = is_max ? fmax(r, red[i]) : (r + red[i]);
+        red[nt] = r;
+    }
+    __syncthreads();
+    return red[nt];
+}
+
+// In-place Cholesky of an n x n SPD matrix (row-major, lower triangle used). Returns false if not PD.
+template <int n>
+CPDP_HD bool chol_inplace(double* A) {
+    for (int j = 0; j < n; ++j) {
+        double d = A[j * n + j];
+        for (int k = 0; k < j; ++k) d -= A[j * n + k] * A[j * n + k];
+        if (!(d > 0.0)) return false;
+        d = sqrt(d);
+        A[j * n + j] = d;
+        for (int i = j + 1; i < n; ++i) {
+            double s = A[i * n + j];
+            for (int k = 0; k < j; ++k) s -= A[i * n + k] * A[j * n + k];
+            A[i * n + j] = s / d;
+        }
+    }
+    return true;
+}
+
+// Solve L L' x = b in place (L from chol_inplace).
+template <int n>
+CPDP_HD void chol_solve(const double* L, double* b) {
+    for (int i = 0; i < n; ++i) {
+        double s = b[i];
+        for (int k = 0; k < i; ++k) s -= L[i * n + k] * b[k];
+        b[i] = s / L[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        double s = b[i];
+        for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * b[k];
+        b[i] = s / L[i * n + i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_newton_step: one CTA per problem.
+//  1. KKT error of the current iterate (stop test, IPOPT-style: max(|grad L|, |g|)).
+//  2. Newton step of the equality-constrained NLP by the Riccati recursion on the stage-wise KKT system, with
+//     IPOPT's inertia-correction schedule when some Quu block is not positive definite.
+//  3. l1-merit backtracking line search (one thread per interval re-integrates the RK4 map).
+//  4. Primal / dual update.
+// ------------------------------------------------------------------------------------------------
+constexpr int NEWTON_THREADS = 64;
+
+CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int N = a.N;
+    const double DT = a.T / a.N / a.S;
+    const double* th = theta_of(a, b);
+    double* X = a.X + (size_t)b * (N + 1) * NX;
+    double* U = a.U + (size_t)b * (N + 1) * NU;
+    double* Lam = a.Lam + (size_t)b * (N + 1) * NX;
+    double* dfc = a.dfc + (size_t)b * (N + 1) * NX;
+    double* dX = a.dX + (size_t)b * (N + 1) * NX;
+    double* dU = a.dU + (size_t)b * N * NU;
+    double* lamn = a.lamn + (size_t)b * (N + 1) * NX;
+    double* Vs = a.Vs + (size_t)b * (N + 1) * NX * NX;
+    double* vs = a.vs + (size_t)b * (N + 1) * NX;
+    const size_t ib = (size_t)b * N;
+
+    CPDP_SHARED double red[NEWTON_THREADS + 1];
+    CPDP_SHARED double s_hx[NX], s_hxx[NX * NX], s_hxe[NX * NP];
+    CPDP_SHARED double s_V[NX * NX], s_v[NX], s_vt[NX];
+    CPDP_SHARED double s_AB[NX * NZ], s_T[NX * NZ], s_Q[NZ * NZ], s_qv[NZ], s_gq[NZ];
+    CPDP_SHARED double s_L[NU * NU], s_K[NU * NX], s_kf[NU];
+    CPDP_SHARED double s_h;
+    CPDP_SHARED int s_flag;
+
+    // ---- terminal cost derivatives, defect of the initial condition
+    if (tid == 0) {
+        double h;
+        Model::term(X + (size_t)N * NX, th, h, s_hx);
+        Model::term2(X + (size_t)N * NX, th, s_hxx, s_hxe);
+        s_h = h;
+    }
+    for (int i = tid; i < NX; i += nt) dfc[i] = a.x0[(size_t)b * NX + i] - X[i];
+    __syncthreads();
+
+    // ---- KKT error and objective
+    double e = 0.0, Jp = 0.0, g1 = 0.0;
+    for (int k = tid; k < N; k += nt) {
+        const double* g = a.gL + (ib + k) * NZ;
+        for (int i = 0; i < NX; ++i) e = fmax(e, fabs(g[i] - Lam[(size_t)k * NX + i]));
+        for (int i = 0; i < NU; ++i) e = fmax(e, fabs(g[NX + i]));
+        Jp += a.cost[ib + k];
+    }
+    for (int i = tid; i < (N + 1) * NX; i += nt) { e = fmax(e, fabs(dfc[i])); g1 += fabs(dfc[i]); }
+    for (int i = tid; i < NX; i += nt) e = fmax(e, fabs(s_hx[i] - Lam[(size_t)N * NX + i]));
+    const double kkt = block_reduce(e, red, true);
+    const double J0 = block_reduce(Jp, red, false) + s_h;
+    g1 = block_reduce(g1, red, false);
+    if (tid == 0) { a.kkt[b] = kkt; a.J[b] = J0; }
+    const int it = a.iters[b];
+    if (!(kkt == kkt)) { if (tid == 0) a.status[b] = ST_NUMERIC; }
+    if (kkt < a.tol || it >= a.max_iter || !(kkt == kkt)) {
+        if (tid == 0 && kkt == kkt) a.status[b] = (kkt < a.tol) ? ST_CONVERGED : ST_MAXITER;
+        for (int i = tid; i < NU; i += nt) U[(size_t)N * NU + i] = U[(size_t)(N - 1) * NU + i];   // CPDP.py:191
+        return;
+    }
+
+    // ---- Riccati factorisation with inertia correction (IPOPT Alg. IC)
+    const double dlast = a.dlast[b];
+    double delta = 0.0;
+    int attempt = 0;
+    while (true) {
+        for (int i = tid; i < NX * NX; i += nt) s_V[i] = s_hxx[i] + ((i / NX == i % NX) ? delta : 0.0);
+        for (int i = tid; i < NX; i += nt) s_v[i] = s_hx[i];
+        if (tid == 0) s_flag = 0;
+        __syncthreads();
+        for (int i = tid; i < NX * NX; i += nt) Vs[(size_t)N * NX * NX + i] = s_V[i];
+        for (int i = tid; i < NX; i += nt) vs[(size_t)N * NX + i] = s_v[i];
+        for (int k = N - 1; k >= 0; --k) {
+            const double* ABg = a.AB + (ib + k) * NX * NZ;
+            const double* Hg = a.H + (ib + k) * NZ * NZ;
+            const double* gLg = a.gL + (ib + k) * NZ;
+            const double* dk1 = dfc + (size_t)(k + 1) * NX;
+            const double* lk1 = Lam + (size_t)(k + 1) * NX;
+            for (int i = tid; i < NX * NZ; i += nt) s_AB[i] = ABg[i];
+            // vt = v + V d_{k+1}
+            for (int i = tid; i < NX; i += nt) {
+                double acc = s_v[i];
+                for (int c = 0; c < NX; ++c) acc += s_V[i * NX + c] * dk1[c];
+                s_vt[i] = acc;
+            }
+            __syncthreads();
+            // T = V [A B];  gq = gL - [A B]' lam_{k+1}
+            for (int i = tid; i < NX * NZ; i += nt) {
+                const int r_ = i / NZ, c = i % NZ;
+                double acc = 0.0;
+                for (int e2 = 0; e2 < NX; ++e2) acc += s_V[r_ * NX + e2] * s_AB[e2 * NZ + c];
+                s_T[i] = acc;
+            }
+            for (int c = tid; c < NZ; c += nt) {
+                double acc = gLg[c];
+                for (int e2 = 0; e2 < NX; ++e2) acc -= s_AB[e2 * NZ + c] * lk1[e2];
+                s_gq[c] = acc;
+            }
+            __syncthreads();
+            // Q = H + delta I + [A B]' T ; qv = gq + [A B]' vt
+            for (int i = tid; i < NZ * NZ; i += nt) {
+                const int r_ = i / NZ, c = i % NZ;
+                double acc = 0.5 * (Hg[r_ * NZ + c] + Hg[c * NZ + r_]) + ((r_ == c) ? delta : 0.0);
+                for (int e2 = 0; e2 < NX; ++e2) acc += s_AB[e2 * NZ + r_] * s_T[e2 * NZ + c];
+                s_Q[i] = acc;
+            }
+            for (int c = tid; c < NZ; c += nt) {
+                double acc = s_gq[c];
+                for (int e2 = 0; e2 < NX; ++e2) acc += s_AB[e2 * NZ + c] * s_vt[e2];
+                s_qv[c] = acc;
+                a.gq[(ib + k) * NZ + c] = s_gq[c];
+            }
+            __syncthreads();
+            // Quu = L L'
+            if (tid == 0) {
+                for (int r_ = 0; r_ < NU; ++r_)
+                    for (int c = 0; c < NU; ++c)
+                        s_L[r_ * NU + c] = 0.5 * (s_Q[(NX + r_) * NZ + NX + c] + s_Q[(NX + c) * NZ + NX + r_]);
+                if (!chol_inplace<NU>(s_L)) s_flag = 1;
+            }
+            __syncthreads();
+            if (s_flag) break;
+            // K = -Quu^{-1} Qux (columns), kf = -Quu^{-1} qu
+            for (int c = tid; c <= NX; c += nt) {
+                double rhs[NU];
+                if (c < NX) { for (int r_ = 0; r_ < NU; ++r_) rhs[r_] = 0.5 * (s_Q[(NX + r_) * NZ + c] + s_Q[c * NZ + NX + r_]); }
+                else { for (int r_ = 0; r_ < NU; ++r_) rhs[r_] = s_qv[NX + r_]; }
+                chol_solve<NU>(s_L, rhs);
+                if (c < NX) { for (int r_ = 0; r_ < NU; ++r_) s_K[r_ * NX + c] = -rhs[r_]; }
+                else { for (int r_ = 0; r_ < NU; ++r_) s_kf[r_] = -rhs[r_]; }
+            }
+            __syncthreads();
+            // V = Qxx + Qxu K (symmetrised), v = qx + Qxu kf
+            for (int i = tid; i < NX * NX; i += nt) {
+                const int r_ = i / NX, c = i % NX;
+                double acc = 0.5 * (s_Q[r_ * NZ + c] + s_Q[c * NZ + r_]);
+                double a1 = 0.0, a2 = 0.0;
+                for (int e2 = 0; e2 < NU; ++e2) {
+                    a1 += 0.5 * (s_Q[r_ * NZ + NX + e2] + s_Q[(NX + e2) * NZ + r_]) * s_K[e2 * NX + c];
+                    a2 += 0.5 * (s_Q[c * NZ + NX + e2] + s_Q[(NX + e2) * NZ + c]) * s_K[e2 * NX + r_];
+                }
+                s_V[i] = acc + 0.5 * (a1 + a2);
+            }
+            for (int i = tid; i < NX; i += nt) {
+                double acc = s_qv[i];
+                for (int e2 = 0; e2 < NU; ++e2) acc += 0.5 * (s_Q[i * NZ + NX + e2] + s_Q[(NX + e2) * NZ + i]) * s_kf[e2];
+                s_v[i] = acc;
+            }
+            for (int i = tid; i < NU * NX; i += nt) a.Kf[(ib + k) * NU * NX + i] = s_K[i];
+            for (int i = tid; i < NU; i += nt) a.kf[(ib + k) * NU + i] = s_kf[i];
+            __syncthreads();
+            for (int i = tid; i < NX * NX; i += nt) Vs[(size_t)k * NX * NX + i] = s_V[i];
+            for (int i = tid; i < NX; i += nt) vs[(size_t)k * NX + i] = s_v[i];
+        }
+        __syncthreads();
+        if (!s_flag) break;
+        // wrong inertia: next delta
+        if (attempt == 0) delta = (dlast == 0.0) ? 1e-4 : fmax(1e-20, dlast / 3.0);
+        else delta *= (dlast == 0.0) ? 100.0 : 8.0;
+        ++attempt;
+        if (delta > 1e40) {
+            if (tid == 0) a.status[b] = ST_NUMERIC;
+            return;
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && delta > 0.0) a.dlast[b] = delta;
+
+    // ---- forward pass: step (dX, dU) and new multipliers
+    for (int i = tid; i < NX; i += nt) dX[i] = dfc[i];
+    __syncthreads();
+    for (int k = 0; k < N; ++k) {
+        const double* Kk = a.Kf + (ib + k) * NU * NX;
+        const double* kfk = a.kf + (ib + k) * NU;
+        const double* dxk = dX + (size_t)k * NX;
+        for (int i = tid; i < NU; i += nt) {
+            double acc = kfk[i];
+            for (int c = 0; c < NX; ++c) acc += Kk[i * NX + c] * dxk[c];
+            dU[(size_t)k * NU + i] = acc;
+        }
+        for (int i = tid; i < NX; i += nt) {
+            double acc = vs[(size_t)k * NX + i];
+            for (int c = 0; c < NX; ++c) acc += Vs[(size_t)k * NX * NX + i * NX + c] * dxk[c];
+            lamn[(size_t)k * NX + i] = acc;
+        }
+        __syncthreads();
+        const double* ABg = a.AB + (ib + k) * NX * NZ;
+        const double* duk = dU + (size_t)k * NU;
+        for (int i = tid; i < NX; i += nt) {
+            double acc = dfc[(size_t)(k + 1) * NX + i];
+            for (int c = 0; c < NX; ++c) acc += ABg[i * NZ + c] * dxk[c];
+            for (int c = 0; c < NU; ++c) acc += ABg[i * NZ + NX + c] * duk[c];
+            dX[(size_t)(k + 1) * NX + i] = acc;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < NX; i += nt) {
+        double acc = vs[(size_t)N * NX + i];
+        for (int c = 0; c < NX; ++c) acc += Vs[(size_t)N * NX * NX + i * NX + c] * dX[(size_t)N * NX + c];
+        lamn[(size_t)N * NX + i] = acc;
+    }
+    __syncthreads();
+
+    // ---- merit function data
+    double lmax = 0.0, gd = 0.0;
+    for (int i = tid; i < (N + 1) * NX; i += nt) lmax = fmax(lmax, fabs(lamn[i]));
+    for (int k = tid; k < N; k += nt) {
+        const double* g = a.gq + (ib + k) * NZ;
+        for (int i = 0; i < NX; ++i) gd += g[i] * dX[(size_t)k * NX + i];
+        for (int i = 0; i < NU; ++i) gd += g[NX + i] * dU[(size_t)k * NU + i];
+    }
+    for (int i = tid; i < NX; i += nt) gd += s_hx[i] * dX[(size_t)N * NX + i];
+    lmax = block_reduce(lmax, red, true);
+    gd = block_reduce(gd, red, false);
+    if (!(lmax == lmax) || !(gd == gd)) { if (tid == 0) a.status[b] = ST_NUMERIC; return; }
+    const double nu = fmax(a.nu[b], 1.1 * lmax);
+    const double phi0 = J0 + nu * g1;
+    const double Dphi = gd - nu * g1;
+
+    // ---- backtracking line search on the l1 merit function
+    double alpha = 1.0;
+    bool ok = false;
+    for (int ls = 0; ls <= 30; ++ls) {
+        double Jt = 0.0, gt = 0.0;
+        for (int k = tid; k <= N; k += nt) {
+            double xk[NX];
+            for (int i = 0; i < NX; ++i) xk[i] = X[(size_t)k * NX + i] + alpha * dX[(size_t)k * NX + i];
+            if (k < N) {
+                double uk[NU], xe[NX], q;
+                for (int i = 0; i < NU; ++i) uk[i] = U[(size_t)k * NU + i] + alpha * dU[(size_t)k * NU + i];
+                rk4_interval(xk, uk, th, DT, a.S, xe, q);
+                Jt += q;
+                for (int i = 0; i < NX; ++i)
+                    gt += fabs(xe[i] - (X[(size_t)(k + 1) * NX + i] + alpha * dX[(size_t)(k + 1) * NX + i]));
+            } else {
+                double h, hx[NX];
+                Model::term(xk, th, h, hx);
+                Jt += h;
+            }
+            if (k == 0) for (int i = 0; i < NX; ++i) gt += fabs(a.x0[(size_t)b * NX + i] - xk[i]);
+        }
+        Jt = block_reduce(Jt, red, false);
+        gt = block_reduce(gt, red, false);
+        const double phit = Jt + nu * gt;
+        if (phit == phit && fabs(phit) < 1e300 && phit <= phi0 + 1e-4 * alpha * Dphi) { ok = true; break; }
+        alpha *= 0.5;
+    }
+    if (!ok) { if (tid == 0) a.status[b] = ST_LINESEARCH; return; }
+
+    // ---- update
+    for (int i = tid; i < (N + 1) * NX; i += nt) {
+        X[i] += alpha * dX[i];
+        Lam[i] += alpha * (lamn[i] - Lam[i]);
+    }
+    for (int i = tid; i < N * NU; i += nt) U[i] += alpha * dU[i];
+    if (tid == 0) { a.nu[b] = nu; a.iters[b] = it + 1; }
+}
+
+CPDP_GLOBAL void __launch_bounds__(NEWTON_THREADS) k_newton_step(SolveArgs a) {
+    const int nact = *a.nact;
+    for (int pi = blockIdx.x; pi < nact; pi += gridDim.x) {
+        newton_step_problem(a, a.act[pi]);
+        __syncthreads();
+    }
+}
+
+// k_solve_init: zero seed (CPDP.py:139,155,167), multipliers 0, per-problem solver state.
+CPDP_GLOBAL void k_solve_init(SolveArgs a) {
+    const size_t tot = (size_t)a.B * (a.N + 1);
+    const size_t gs = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot * NX; i += gs) { a.X[i] = 0.0; a.Lam[i] = 0.0; }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot * NU; i += gs) a.U[i] = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)a.B; i += gs) {
+        a.status[i] = ST_RUNNING; a.iters[i] = 0; a.nu[i] = 0.0; a.dlast[i] = 0.0; a.J[i] = 0.0; a.kkt[i] = 0.0;
+    }
+}
+
+// k_compact: ordered list of the problems that are still iterating (single CTA).
+constexpr int COMPACT_THREADS = 256;
+CPDP_GLOBAL void __launch_bounds__(COMPACT_THREADS) k_compact(SolveArgs a) {
+    CPDP_SHARED int s_cnt[COMPACT_THREADS + 1];
+    const int tid = threadIdx.x;
+    const int chunk = (a.B + COMPACT_THREADS - 1) / COMPACT_THREADS;
+    const int lo = tid * chunk, hi = (lo + chunk < a.B) ? lo + chunk : a.B;
+    int c = 0;
+    for (int i = lo; i < hi; ++i) c += (a.status[i] == ST_RUNNING);
+    s_cnt[tid] = c;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int i = 0; i < COMPACT_THREADS; ++i) { const int v = s_cnt[i]; s_cnt[i] = run; run += v; }
+        s_cnt[COMPACT_THREADS] = run;
+        *a.nact = run;
+    }
+    __syncthreads();
+    int o = s_cnt[tid];
+    for (int i = lo; i < hi; ++i) if (a.status[i] == ST_RUNNING) a.act[o++] = i;
+}
+
+}  // namespace cpdp

@@ -1,0 +1,32 @@
+// Portability shim: lets the CUDA kernels in cpdp_kernels.cuh also compile with g++ for the host
+// emulation harness under tests/emu/ (one std::thread per CUDA thread, std::barrier for __syncthreads,
+// optionally under ThreadSanitizer).  The shipped library is ALWAYS built with nvcc for sm_100a; the
+// host branch exists only so that kernel logic can be checked in a container that has no GPU.
+#pragma once
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define CPDP_HD __host__ __device__ __forceinline__
+#define CPDP_D __device__ __forceinline__
+#define CPDP_GLOBAL __global__
+#define CPDP_SHARED __shared__
+#else
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#define CPDP_HD inline
+#define CPDP_D inline
+#define CPDP_GLOBAL
+#define CPDP_SHARED static
+#define __restrict__ __restrict
+#define __launch_bounds__(...)
+struct cpdp_emu_dim3 { int x, y, z; };
+extern thread_local cpdp_emu_dim3 threadIdx;
+extern cpdp_emu_dim3 blockIdx, blockDim, gridDim;
+void cpdp_emu_syncthreads();
+extern double* cpdp_emu_dyn_smem;
+#define __syncthreads() cpdp_emu_syncthreads()
+typedef void* cudaStream_t;
+using std::fmax; using std::fmin; using std::fabs; using std::sqrt; using std::pow;
+#endif
