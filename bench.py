@@ -1,0 +1,335 @@
+#!/usr/bin/env python3
+"""Benchmark of the CPDP gradient iteration (BASELINE.json metric: OCP gradient-iterations per second on batched
+quadrotor OCPs, n_grid 50).
+
+  python bench.py --gpus N --steps K --warmup W              our CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W      the CPU oracle (stand-in for the reference's
+                                                             CasADi/IPOPT/scipy path, which cannot run in this image)
+
+One "step" = one CPDP gradient iteration for every OCP of the batch: forward solve from the zero seed, auxiliary
+system (backward Riccati + forward sweep), loss and dL/dtheta, and the fixed-order cross-problem reduction.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "CPDP OCP gradient-iterations per second (batched quadrotor OCPs, n_grid 50)"
+UNIT = "ocp_grad_iters/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="OCPs per GPU (weak scaling) or in total (--scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--n-grid", type=int, default=50)
+    ap.add_argument("--mode", default=None, choices=["bdf", "rk45"], help="backward Riccati integrator")
+    ap.add_argument("--rtol", type=float, default=1e-3)
+    ap.add_argument("--atol", type=float, default=1e-6)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = one per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle) — the ONLY place besides tests/ and smoke() that touches oracle/
+# ----------------------------------------------------------------------------------------------------------------
+_ORC = None
+
+
+def _cpu_init(n_grid):
+    global _ORC
+    from oracle import models
+    from oracle.cpdp_oracle import Oracle
+    _ORC = Oracle(models.quadrotor(), n_grid=n_grid)
+
+
+def _cpu_one(job):
+    x0, goal, theta, taus, wp = job
+    _ORC.pd = goal
+    loss, dl, ex = _ORC.grad_iter(x0, 1.0, theta, taus, wp)       # as-shipped: BDF backward, RK45 forward
+    return loss, dl, ex["info"]["iters"]
+
+
+def cpu_baseline(n_grid, sample, steps=1, warmup=0):
+    """Oracle on `sample` problems of the same synthetic batch with one process per host core."""
+    from multiprocessing import Pool
+    from lfsd_b200 import synthetic
+    cores = os.cpu_count() or 1
+    sample = sample or cores
+    qb = synthetic.quad_batch(max(sample, 1))
+    jobs = [(qb["x0"][b], qb["goal"][b], qb["theta"], qb["taus"], qb["wp"][b]) for b in range(sample)]
+    with Pool(min(cores, sample), initializer=_cpu_init, initargs=(n_grid,)) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_one, jobs[:min(cores, sample)])
+        t0 = time.time()
+        for _ in range(steps):
+            res = pool.map(_cpu_one, jobs)
+        dt = time.time() - t0
+    value = sample * steps / dt
+    return dict(value=value, unit=UNIT, cores=min(cores, sample), kind="port",
+                sample="%d OCPs (first indices of the seeded 4096-OCP batch), n_grid %d, %d step(s), %.1f s wall; "
+                       "oracle = numpy/scipy restatement (Newton-KKT + scipy BDF/RK45 as-shipped), one process per core"
+                       % (sample, n_grid, steps, dt)), dt, steps
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def flop_model(info, n, m, r, N, S, iters_sum, B, counters_sum, mode):
+    """Executed useful fp64 flops of one step: op counts of the generated model code after CSE plus
+    the dense/sparse linear algebra around it, times the Newton-iteration / rhs-evaluation counters the kernels record."""
+    nz = n + m
+    stages = 4 * S
+    per_int = stages * (2 * info["ops_fc"] + info["ops_hgrad"] + 8 * n)                     # k_stage_adjoint
+    per_int += stages * nz * (info["ops_dir"] + 2 * nz * n + 6 * n)                         # k_stage_hessian
+    per_int += 2 * n * n * nz + 2 * nz * nz * n + 2 * m * m * (n + 1) + 2 * n * n * m + 4 * n * nz + stages * info["ops_fc"]
+    solve = iters_sum * N * per_int
+    nnzx, nnzu = info["nnz_fx"], info["nnz_fu"]
+    ric = info["ops_pmp"] + 2 * nnzu * (n + r) + 2 * m * m * n + (n * (n + 1) // 2) * (4 * nnzx / n * 1.0 + 4 * m) \
+        + n * r * (2 * nnzx / n + 2 + 2 * m)
+    fwd = info["ops_pmp"] + 2 * nnzu * (n + r) + 2 * m * m * (n + r) + 2 * m * n * r + n * r * (2 * nnzx / n + 2 * nnzu / n + 1) \
+        + 4 * (n * (n + 1) // 2 + n * r)
+    ny_r, ny_f = n * (n + 1) // 2 + n * r, n * r
+    aux = counters_sum[0] * (ric + 16 * ny_r) + counters_sum[2] * (fwd + 16 * ny_f)
+    return dict(solve=float(solve), aux=float(aux), total=float(solve + aux))
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import lfsd_b200
+    from lfsd_b200 import standard, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B_total = a.batch * world if a.scaling == "weak" else a.batch
+    lo, hi = synthetic.shard_bounds(B_total, world, rank)
+    Bl = hi - lo
+
+    oc = standard.quadrotor_oc(n_grid=a.n_grid)
+    lib = oc.build(name=oc.lib_name)
+    mode = a.mode or ("bdf" if hasattr(lib.L, "cpdp_has_bdf") else "rk45")
+    oc.aux_mode = oc.MODE_BDF if mode == "bdf" else oc.MODE_RK45
+    oc.rtol_back, oc.atol_back = a.rtol, a.atol
+    qb = synthetic.quad_batch(B_total)
+    # pinned host buffers (the e2e leg copies them every step)
+    host = {k: torch.from_numpy(np.ascontiguousarray(qb[k][lo:hi])).pin_memory() for k in ("x0", "goal", "wp")}
+    host["taus"] = torch.from_numpy(qb["taus"]).pin_memory()
+    host["theta"] = torch.from_numpy(qb["theta"]).pin_memory()
+    h2d_bytes = sum(v.numel() * 8 for v in host.values())
+    resident = {k: v.to(dev) for k, v in host.items()}
+    r = oc.n_auxvar
+    gathered = torch.empty((B_total, r + 1), dtype=torch.float64, device=dev)
+    result_host = torch.empty((r + 1,), dtype=torch.float64).pin_memory()
+    stats = {}
+
+    def step(inp):
+        sol = oc.cocSolverBatch(inp["x0"], 1.0, inp["theta"], pdata=inp["goal"])
+        stats["rounds"] = lib.last_rounds()
+        aux = oc.auxSysSolverBatch(sol, inp["taus"], inp["wp"], qb["sel"])
+        rows = torch.cat([aux["loss"].unsqueeze(1), aux["dtheta"]], dim=1)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rows)     # the single exchange of the iteration (64 B / OCP)
+            allrows = gathered
+        else:
+            allrows = rows
+        red = oc.reduceBatch(allrows[:, 0].contiguous(), allrows[:, 1:].contiguous())
+        return red, sol, aux
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        red, sol, aux = step(resident)
+    sync_all()
+
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ph = []
+    sync_all()
+    ev[0].record()
+    for _ in range(a.steps):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        sol = oc.cocSolverBatch(resident["x0"], 1.0, resident["theta"], pdata=resident["goal"])
+        e1.record()
+        aux = oc.auxSysSolverBatch(sol, resident["taus"], resident["wp"], qb["sel"])
+        rows = torch.cat([aux["loss"].unsqueeze(1), aux["dtheta"]], dim=1)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rows)
+            allrows = gathered
+        else:
+            allrows = rows
+        red = oc.reduceBatch(allrows[:, 0].contiguous(), allrows[:, 1:].contiguous())
+        e2.record()
+        ph.append((e0, e1, e2))
+    ev[1].record()
+    sync_all()
+    ms = ev[0].elapsed_time(ev[1])
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    solve_ms = float(np.mean([p[0].elapsed_time(p[1]) for p in ph]))
+    aux_ms = float(np.mean([p[1].elapsed_time(p[2]) for p in ph]))
+    rounds = lib.last_rounds()
+
+    # ---- timed region 2: end to end through the public API with HOST buffers ---------------------------------
+    sync_all()
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev2[0].record()
+    for _ in range(a.steps):
+        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        red, sol, aux = step(inp)
+        result_host.copy_(red, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller consumes loss / gradient on the host
+    ev2[1].record()
+    sync_all()
+    t2 = torch.tensor([ev2[0].elapsed_time(ev2[1])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t2.item())
+
+    # ---- statistics -----------------------------------------------------------------------------------------
+    status = sol["status"].cpu().numpy()
+    iters = sol["iters"].cpu().numpy()
+    cnt = aux["counters"].cpu().numpy().astype(np.int64)
+    loc = torch.tensor([float(iters.sum()), float((status != 1).sum()), float((aux["aux_status"] != 0).sum().item())]
+                       + [float(x) for x in cnt.sum(0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(loc)
+    loc = loc.cpu().numpy()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    info = oc.codegen_info
+    fm = flop_model(info, oc.n_state, oc.n_control, r, a.n_grid, oc.steps_per_grid, loc[0], B_total, loc[3:7], mode)
+    step_s = ms / a.steps / 1e3
+    value = B_total * a.steps / (ms / 1e3)
+    peak_tf = 148 * 64 * 2 * 1.965e9 / 1e12        # nominal B200 DFMA peak (no fp64 entry in MEASURED_PEAKS.json)
+    achieved_tf = fm["total"] / world / step_s / 1e12
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%d quadrotor OCPs%s (n=13,m=4,r=7), n_grid %d, S=4, T=1, shared theta0, "
+                               "rng default_rng(20210308); SURVEY.md 8d" % (a.batch, " per GPU" if a.scaling == "weak" else " total", a.n_grid),
+                   "global_batch": B_total, "aux_mode": mode, "rtol_back": a.rtol, "atol_back": a.atol,
+                   "parallelism": "dp%d contiguous shards, all-gather of per-OCP (loss,dtheta) rows + fixed-tree sum" % world,
+                   "l2": "per-step working set (~%.1f GB workspace) exceeds the 126 MB L2" % (lib.workspace_bytes(Bl, a.n_grid, 4) / 1e9)},
+        "e2e": {"value": B_total * a.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": (r + 1) * 8},
+        "gpu_launches": a.steps * (2 + 4 * rounds + 2 + 1),
+        "clocks": clocks,
+        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved_tf / peak_tf, "traffic": None,
+                     "note": "whole-step executed fp64 flops (DESIGN.md flop model x recorded Newton-iteration / rhs counters) "
+                             "per GPU / step time; peak = nominal 148 SM x 64 DFMA x 2 x 1.965 GHz (MEASURED_PEAKS.json has no fp64 figure)",
+                     "flops_per_step": fm, "phase_ms": {"solve": solve_ms, "aux_loss_reduce": aux_ms}},
+        "stats": {"newton_iters_mean": loc[0] / B_total, "newton_rounds": rounds, "not_converged": int(loc[1]),
+                  "aux_failed": int(loc[2]), "back_rhs_mean": loc[3] / B_total, "back_steps_mean": loc[4] / B_total,
+                  "fwd_rhs_mean": loc[5] / B_total, "fwd_steps_mean": loc[6] / B_total,
+                  "loss_sum": float(red[0].item())},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        cb, _, _ = cpu_baseline(a.n_grid, a.cpu_sample)
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import lfsd_b200  # noqa: F401
+    cb, dt, steps = cpu_baseline(a.n_grid, a.cpu_sample, steps=a.steps, warmup=min(a.warmup, 1))
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": a.scaling,
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "%d quadrotor OCPs per step (bounded sample of the 4096-OCP batch), n_grid %d" % (cb["cores"], a.n_grid),
+                      "note": "the reference's CasADi/IPOPT path cannot run in this image (no casadi); this is the CPU oracle port"},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

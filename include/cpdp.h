@@ -1,0 +1,77 @@
+/* cpdp.h — C ABI of the B200 CPDP gradient-iteration library (one shared object per model:
+ * libcpdp_<model>.so, built from learning-from-sparse-demonstrations_b200/csrc/cpdp_lib.cu).
+ *
+ * The reference has no FFI: the path sits behind Python methods of COCSys.  Each entry point below replaces
+ * the numerical body of one of them; the Python class lfsd_b200.CPDP.COCSys binds them with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions: all arrays are row-major IEEE fp64 DEVICE pointers owned by the caller unless marked (host);
+ * n = states, m = controls, r = learnable parameters (cpdp_model_dims), B problems, N grid intervals,
+ * S RK4 sub-steps per interval.  Calls are stream-ordered on `stream` (a cudaStream_t passed as void*), hold no
+ * state between calls, and return 0, a negative argument-error code or a positive cudaError_t
+ * (cpdp_error_string).  Numerical outcomes are reported per problem in status arrays, never as return codes.
+ */
+#ifndef CPDP_H
+#define CPDP_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* per-problem solver status written by cpdp_solve */
+enum { CPDP_RUNNING = 0, CPDP_CONVERGED = 1, CPDP_MAXITER = 2, CPDP_LINESEARCH = 3, CPDP_NUMERIC = 4 };
+
+/* Model dimensions compiled into this library (COCSys.n_state / n_control / n_auxvar, CPDP.py:17,22,36);
+ * q = number of per-problem constants (pdata, e.g. a goal position), 0 for most models. */
+int cpdp_model_dims(int* n, int* m, int* r, int* q);
+
+/* Length of one packed Riccati node [upper-tri(P) | W] = n(n+1)/2 + n*r (internal table of auxSysSolver). */
+int cpdp_riccati_state_dim(void);
+
+/* Bytes of scratch the caller must provide to cpdp_solve / cpdp_aux for (B, N, S). */
+size_t cpdp_workspace_bytes(int B, int N, int S);
+
+/* Replaces COCSys.cocSolver (CPDP.py:92-198) for B problems: RK4 multiple-shooting NLP, all-zeros seed,
+ * Newton-KKT with inertia correction and l1-merit line search.
+ *   x0[B][n]; theta[B][r] (theta_stride = r) or shared theta[r] (theta_stride = 0); T horizon;
+ *   tol: KKT tolerance; max_iter: Newton iteration cap;
+ *   rounds > 0: launch exactly that many Newton rounds with no host synchronisation (CUDA-graph capturable);
+ *   rounds = 0: poll the number of unconverged problems (one stream sync per round) and stop early.
+ * Outputs X[B][N+1][n], U[B][N+1][m] (row N copies row N-1, CPDP.py:191), Lam[B][N+1][n] (= lam_g, CPDP.py:193),
+ * status[B], iters[B]; optional kkt_out[B], cost_out[B]. */
+int cpdp_solve(void* ws, size_t ws_bytes, int B, int N, int S, double T,
+               const double* x0, const double* theta, int theta_stride, const double* pdata /* [B][q] or NULL */,
+               double tol, int max_iter, int rounds,
+               double* X, double* U, double* Lam, int* status, int* iters,
+               double* kkt_out, double* cost_out, void* stream);
+
+/* Newton rounds launched by the most recent cpdp_solve of this process (4 kernel launches per round + 2). */
+int cpdp_last_rounds(void);
+
+/* Replaces COCSys.auxSysSolver (CPDP.py:301-381) and the getloss_*corrections closures
+ * (lib/QuadAlgorithm.py:616-639, Examples/rocket_groundtruth.py:45-70) for B problems.
+ *   mode 0: backward Riccati sweep by RK45 with (rtol_b, atol_b)   [what COCSys_TimeVarying does, CPDP.py:740]
+ *   mode 1: backward sweep by the BDF scheme of the as-shipped COCSys (CPDP.py:335), scipy defaults in rtol_b/atol_b
+ *   forward sweep: RK45 with (rtol_f, atol_f) (CPDP.py:368; scipy defaults 1e-3 / 1e-6).
+ *   Loss: W waypoints of D observed state components sel[D] (host ints); taus[B][W] (taus_stride = W) or shared
+ *   taus[W] (stride 0); wp[B][W][D].  W = 0 skips the loss.
+ * Outputs Xa[B][N+1][n*r] (dx/dtheta nodes), Ua[B][N+1][m*r], loss[B], dtheta[B][r] (reference convention:
+ * dl_dy = y - wp, i.e. half the true gradient), aux_status[B] (0 ok), counters[B][4]
+ * (backward rhs evals, backward steps, forward rhs evals, forward steps). */
+int cpdp_aux(void* ws, size_t ws_bytes, int B, int N, int S, double T,
+             const double* theta, int theta_stride, const double* pdata,
+             const double* X, const double* U, const double* Lam, const int* solve_status,
+             int mode, double rtol_b, double atol_b, double rtol_f, double atol_f,
+             int W, int D, const int* sel /* host */, const double* taus, int taus_stride, const double* wp,
+             double* Xa, double* Ua, double* loss, double* dtheta, int* aux_status, int* counters, void* stream);
+
+/* Cross-problem sum of [loss | dL/dtheta] rows in a fixed binary tree over the row index (bit-identical for any
+ * sharding of the rows over GPUs once they are all-gathered).  scratch: nextpow2(B)*(1+r) doubles; out[1+r]. */
+int cpdp_reduce(const double* loss, const double* dtheta, int B, double* scratch, double* out, void* stream);
+
+const char* cpdp_error_string(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

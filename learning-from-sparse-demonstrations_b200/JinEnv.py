@@ -68,8 +68,16 @@ def _omega(w):
                    horzcat(w[2], w[1], -w[0], 0))
 
 
+def _as_vec(v):
+    """list / ndarray / SX -> SX column; entries may be numbers or symbols (a symbolic goal becomes per-problem
+    data of the batched solver, see COCSys.setProblemVariable)."""
+    if isinstance(v, SX):
+        return v
+    return vertcat(*list(v))
+
+
 def _sq_err(vec, goal):
-    d = vec - np.asarray(goal, dtype=float)
+    d = vec - _as_vec(goal)
     return dot(d, d)
 
 
@@ -247,10 +255,10 @@ class Quadrotor(_RigidBody6DoF):
         self.U = self.T_B
 
     def _goal_terms(self, goal: QuadStates):
-        self._goal_r = np.asarray(goal.position, dtype=float)
-        self._goal_v = np.asarray(goal.velocity, dtype=float)
-        self._goal_w = np.asarray(goal.angular_velocity, dtype=float)
-        goal_R = self.dir_cosine(vertcat(*goal.attitude_quaternion))
+        self._goal_r = _as_vec(goal.position)
+        self._goal_v = _as_vec(goal.velocity)
+        self._goal_w = _as_vec(goal.angular_velocity)
+        goal_R = self.dir_cosine(_as_vec(goal.attitude_quaternion))
         att = trace(np.identity(3) - mtimes(transpose(goal_R), self.dir_cosine(self.q)))
         return att
 

@@ -1,0 +1,131 @@
+"""ctypes binding of the C ABI in ``include/cpdp.h`` and the nvcc build of one model library.
+
+The library is the product path: nothing here falls back to a CPU implementation.  If the shared object is
+missing it is compiled with nvcc for sm_100a (in-tree, under ``lib/``); if that is impossible the call raises.
+"""
+import ctypes
+import hashlib
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_PKG, "csrc")
+GEN_DIR = os.path.join(CSRC, "generated")
+LIB_DIR = os.path.join(_PKG, "lib")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
+
+STATUS_NAMES = {0: "running", 1: "converged", 2: "max_iter", 3: "linesearch_fail", 4: "numeric"}
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_d = ctypes.c_double
+_sz = ctypes.c_size_t
+
+
+class CpdpError(RuntimeError):
+    pass
+
+
+def _sources_digest():
+    h = hashlib.sha1()
+    for fn in sorted(os.listdir(CSRC)):
+        p = os.path.join(CSRC, fn)
+        if os.path.isfile(p):
+            h.update(fn.encode())
+            with open(p, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def build_model_library(name, header_text, force=False, verbose=False):
+    """Writes csrc/generated/model_<name>.cuh and compiles lib/libcpdp_<name>.so (skipped when up to date)."""
+    os.makedirs(GEN_DIR, exist_ok=True)
+    os.makedirs(LIB_DIR, exist_ok=True)
+    hdr = os.path.join(GEN_DIR, "model_%s.cuh" % name)
+    so = os.path.join(LIB_DIR, "libcpdp_%s.so" % name)
+    stamp = so + ".stamp"
+    digest = hashlib.sha1((header_text + _sources_digest() + " ".join(NVCC_FLAGS)).encode()).hexdigest()
+    if not force and os.path.exists(so) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return so
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise CpdpError("libcpdp_%s.so is missing and nvcc was not found; the CUDA extension is required "
+                        "(there is no CPU fallback)" % name)
+    with open(hdr, "w") as f:
+        f.write(header_text)
+    ns = "cpdp_" + "".join(ch if ch.isalnum() else "_" for ch in name)
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", CSRC, "-DCPDP_NS=%s" % ns, "-DCPDP_MODEL_HEADER=\"%s\"" % hdr,
+                                 os.path.join(CSRC, "cpdp_lib.cu"), "-o", so]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise CpdpError("nvcc failed for model %s:\n%s\n%s" % (name, r.stdout, r.stderr))
+    if verbose:
+        print(r.stderr)
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return so
+
+
+class CpdpLib:
+    """Thin typed wrapper over one libcpdp_<model>.so.  All pointer arguments are integer addresses."""
+
+    def __init__(self, so_path):
+        if not os.path.exists(so_path):
+            raise CpdpError("CUDA extension %s not found (no CPU fallback exists)" % so_path)
+        self.path = so_path
+        L = self.L = ctypes.CDLL(so_path)
+        L.cpdp_model_dims.argtypes = [ctypes.POINTER(_i)] * 4
+        L.cpdp_model_dims.restype = _i
+        L.cpdp_riccati_state_dim.restype = _i
+        L.cpdp_last_rounds.restype = _i
+        L.cpdp_workspace_bytes.argtypes = [_i, _i, _i]
+        L.cpdp_workspace_bytes.restype = _sz
+        L.cpdp_solve.argtypes = [_vp, _sz, _i, _i, _i, _d, _vp, _vp, _i, _vp, _d, _i, _i,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.cpdp_solve.restype = _i
+        L.cpdp_aux.argtypes = [_vp, _sz, _i, _i, _i, _d, _vp, _i, _vp, _vp, _vp, _vp, _vp,
+                               _i, _d, _d, _d, _d, _i, _i, ctypes.POINTER(_i), _vp, _i, _vp,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.cpdp_aux.restype = _i
+        L.cpdp_reduce.argtypes = [_vp, _vp, _i, _vp, _vp, _vp]
+        L.cpdp_reduce.restype = _i
+        if hasattr(L, "cpdp_error_string"):
+            L.cpdp_error_string.argtypes = [_i]
+            L.cpdp_error_string.restype = ctypes.c_char_p
+        n, m, r, q = _i(), _i(), _i(), _i()
+        L.cpdp_model_dims(ctypes.byref(n), ctypes.byref(m), ctypes.byref(r), ctypes.byref(q))
+        self.n, self.m, self.r, self.q = n.value, m.value, r.value, q.value
+        self.nyr = L.cpdp_riccati_state_dim()
+
+    def check(self, rc, what):
+        if rc != 0:
+            msg = self.L.cpdp_error_string(rc).decode() if hasattr(self.L, "cpdp_error_string") else ""
+            raise CpdpError("%s failed with code %d (%s)" % (what, rc, msg))
+
+    def last_rounds(self):
+        return int(self.L.cpdp_last_rounds())
+
+    def workspace_bytes(self, B, N, S):
+        return int(self.L.cpdp_workspace_bytes(B, N, S))
+
+    def solve(self, ws, ws_bytes, B, N, S, T, x0, theta, theta_stride, pdata, tol, max_iter, rounds,
+              X, U, Lam, status, iters, kkt, cost, stream):
+        self.check(self.L.cpdp_solve(ws, ws_bytes, B, N, S, T, x0, theta, theta_stride, pdata, tol, max_iter, rounds,
+                                     X, U, Lam, status, iters, kkt, cost, stream), "cpdp_solve")
+
+    def aux(self, ws, ws_bytes, B, N, S, T, theta, theta_stride, pdata, X, U, Lam, solve_status,
+            mode, rtol_b, atol_b, rtol_f, atol_f, W, D, sel, taus, taus_stride, wp,
+            Xa, Ua, loss, dtheta, aux_status, counters, stream):
+        sel_arr = (_i * max(1, len(sel)))(*sel) if sel else (_i * 1)(0)
+        self.check(self.L.cpdp_aux(ws, ws_bytes, B, N, S, T, theta, theta_stride, pdata, X, U, Lam, solve_status,
+                                   mode, rtol_b, atol_b, rtol_f, atol_f, W, D, sel_arr, taus, taus_stride, wp,
+                                   Xa, Ua, loss, dtheta, aux_status, counters, stream), "cpdp_aux")
+
+    def reduce(self, loss, dtheta, B, scratch, out, stream):
+        self.check(self.L.cpdp_reduce(loss, dtheta, B, scratch, out, stream), "cpdp_reduce")

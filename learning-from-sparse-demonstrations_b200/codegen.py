@@ -92,16 +92,19 @@ def _sparse_tables(name, M):
                       "    static constexpr int %s_nnz = %d;" % (name, len(colidx))])
 
 
-def generate_model_header(name, state, control, auxvar, dyn, path_cost, final_cost):
-    """Returns (header_text, info dict).  All arguments are SX / sympy matrices / scalars."""
+def generate_model_header(name, state, control, auxvar, dyn, path_cost, final_cost, pdata=None):
+    """Returns (header_text, info dict).  All arguments are SX / sympy matrices / scalars.
+    ``pdata``: optional per-problem constants (e.g. a goal position) that are not learnable."""
     x, u, th = _vec(state), _vec(control), _vec(auxvar)
+    pdv = _vec(pdata) if pdata is not None else []
     n, m, r = len(x), len(u), len(th)
+    nq = len(pdv)
     nz = n + m
     f = sp.Matrix(_vec(dyn))
     c = _to_matrix(path_cost)[0, 0]
     h = _to_matrix(final_cost)[0, 0]
     assert f.shape[0] == n
-    extra = (f.free_symbols | c.free_symbols | h.free_symbols) - set(x) - set(u) - set(th)
+    extra = (f.free_symbols | c.free_symbols | h.free_symbols) - set(x) - set(u) - set(th) - set(pdv)
     assert not extra, "free symbols that are neither state, control nor auxvar: %s" % extra
     assert not (h.free_symbols & set(u)), "final cost must not depend on the control"
 
@@ -109,7 +112,8 @@ def generate_model_header(name, state, control, auxvar, dyn, path_cost, final_co
     xs = [sp.Symbol("x[%d]" % i, real=True) for i in range(n)]
     us = [sp.Symbol("u[%d]" % i, real=True) for i in range(m)]
     ts = [sp.Symbol("th[%d]" % i, real=True) for i in range(r)]
-    sub = dict(zip(x + u + th, xs + us + ts))
+    ps = [sp.Symbol("pd[%d]" % i, real=True) for i in range(nq)]
+    sub = dict(zip(x + u + th + pdv, xs + us + ts + ps))
     f = f.subs(sub); c = c.subs(sub); h = h.subs(sub)
     z = xs + us
     mus = [sp.Symbol("mu[%d]" % i, real=True) for i in range(n)]
@@ -127,12 +131,12 @@ def generate_model_header(name, state, control, auxvar, dyn, path_cost, final_co
     parts = []
     body, info["ops_fc"] = _emit_body([("f[%d]" % i, f[i]) for i in range(n)] + [("c", c)])
     parts.append("    CPDP_HD static void fc(const double* __restrict__ x, const double* __restrict__ u, "
-                 "const double* __restrict__ th, double* __restrict__ f, double& c) {\n%s\n    }" % body)
+                 "const double* __restrict__ th, const double* __restrict__ pd, double* __restrict__ f, double& c) {\n%s\n    }" % body)
 
     body, info["ops_hgrad"] = _emit_body([("gx[%d]" % i, Hz[i]) for i in range(n)] +
                                          [("gu[%d]" % i, Hz[n + i]) for i in range(m)])
     parts.append("    CPDP_HD static void hgrad(const double* __restrict__ x, const double* __restrict__ u, "
-                 "const double* __restrict__ th, const double* __restrict__ mu, const double w, "
+                 "const double* __restrict__ th, const double* __restrict__ pd, const double* __restrict__ mu, const double w, "
                  "double* __restrict__ gx, double* __restrict__ gu) {\n%s\n    }" % body)
 
     df = fz * dz
@@ -140,7 +144,7 @@ def generate_model_header(name, state, control, auxvar, dyn, path_cost, final_co
     body, info["ops_dir"] = _emit_body([("df[%d]" % i, df[i]) for i in range(n)] +
                                        [("hz[%d]" % i, hz[i]) for i in range(nz)])
     parts.append("    CPDP_HD static void dir(const double* __restrict__ x, const double* __restrict__ u, "
-                 "const double* __restrict__ th, const double* __restrict__ mu, const double w, "
+                 "const double* __restrict__ th, const double* __restrict__ pd, const double* __restrict__ mu, const double w, "
                  "const double* __restrict__ dx, const double* __restrict__ du, "
                  "double* __restrict__ df, double* __restrict__ hz) {\n%s\n    }" % body)
 
@@ -164,32 +168,34 @@ def generate_model_header(name, state, control, auxvar, dyn, path_cost, final_co
     body, info["ops_pmp"] = _emit_body(assigns)
     body = body.replace("mu[", "lam[")
     parts.append("    CPDP_HD static void pmp(const double* __restrict__ x, const double* __restrict__ u, "
-                 "const double* __restrict__ lam, const double* __restrict__ th, double* __restrict__ M) {\n%s\n    }" % body)
+                 "const double* __restrict__ lam, const double* __restrict__ th, const double* __restrict__ pd, double* __restrict__ M) {\n%s\n    }" % body)
     info["pmp_nnz"] = len(assigns)
 
     hx = sp.Matrix([h]).jacobian(xs)
     body, info["ops_term"] = _emit_body([("h", h)] + [("hx[%d]" % i, hx[i]) for i in range(n)])
-    parts.append("    CPDP_HD static void term(const double* __restrict__ x, const double* __restrict__ th, "
+    parts.append("    CPDP_HD static void term(const double* __restrict__ x, const double* __restrict__ th, const double* __restrict__ pd, "
                  "double& h, double* __restrict__ hx) {\n%s\n    }" % body)
     hxx = hx.jacobian(xs)
     hxe = hx.jacobian(ts)
     body, info["ops_term2"] = _emit_body([("hxx[%d]" % (i * n + j), hxx[i, j]) for i in range(n) for j in range(n)] +
                                          [("hxe[%d]" % (i * r + j), hxe[i, j]) for i in range(n) for j in range(r)])
-    parts.append("    CPDP_HD static void term2(const double* __restrict__ x, const double* __restrict__ th, "
+    parts.append("    CPDP_HD static void term2(const double* __restrict__ x, const double* __restrict__ th, const double* __restrict__ pd, "
                  "double* __restrict__ hxx, double* __restrict__ hxe) {\n%s\n    }" % body)
 
     tables = "\n".join([_sparse_tables("FX", mats[0][1]), _sparse_tables("FU", mats[1][1]),
                         _sparse_tables("FE", mats[2][1])])
-    info.update(n=n, m=m, r=r, nnz_fx=sum(1 for e in mats[0][1] if e != 0),
+    info.update(n=n, m=m, r=r, nq=nq, nnz_fx=sum(1 for e in mats[0][1] if e != 0),
                 nnz_fu=sum(1 for e in mats[1][1] if e != 0))
 
     text = """// GENERATED by lfsd_b200/codegen.py -- do not edit.  model: {name}
 // n={n} m={m} r={r}; op counts after CSE: fc={ops_fc} hgrad={ops_hgrad} dir={ops_dir} pmp={ops_pmp} ({pmp_nnz} nnz)
 #pragma once
+#include "cpdp_port.h"
 struct Model {{
     static constexpr int NX = {n};
     static constexpr int NU = {m};
     static constexpr int NP = {r};
+    static constexpr int NQ = {nq};
     static constexpr int NZ = {nz};
 {offs}
 {tables}

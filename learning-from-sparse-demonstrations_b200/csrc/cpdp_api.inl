@@ -10,7 +10,7 @@
 #include <cstddef>
 #include <cstdint>
 
-namespace cpdp {
+namespace CPDP_NS {
 
 struct WsLayout {
     SolveArgs sa;
@@ -54,38 +54,45 @@ static WsLayout ws_carve(char* base, int B, int N, int S) {
     return w;
 }
 
-}  // namespace cpdp
+}  // namespace CPDP_NS
+
+static int g_last_rounds = 0;
 
 extern "C" {
 
-int cpdp_model_dims(int* n, int* m, int* r) {
-    if (n) *n = cpdp::NX;
-    if (m) *m = cpdp::NU;
-    if (r) *r = cpdp::NP;
+// Newton rounds launched by the most recent cpdp_solve call of this process (each round = 4 kernel launches).
+CPDP_API int cpdp_last_rounds(void) { return g_last_rounds; }
+
+CPDP_API int cpdp_model_dims(int* n, int* m, int* r, int* q) {
+    if (q) *q = CPDP_NS::NQ;
+    if (n) *n = CPDP_NS::NX;
+    if (m) *m = CPDP_NS::NU;
+    if (r) *r = CPDP_NS::NP;
     return 0;
 }
 
-int cpdp_riccati_state_dim(void) { return cpdp::NYR; }
+CPDP_API int cpdp_riccati_state_dim(void) { return CPDP_NS::NYR; }
 
-size_t cpdp_workspace_bytes(int B, int N, int S) {
+CPDP_API size_t cpdp_workspace_bytes(int B, int N, int S) {
     if (B <= 0 || N <= 0 || S <= 0) return 0;
-    return cpdp::ws_carve(nullptr, B, N, S).bytes;
+    return CPDP_NS::ws_carve(nullptr, B, N, S).bytes;
 }
 
 // Forward optimal-control solve for B problems (COCSys.cocSolver, CPDP.py:92-198).
-int cpdp_solve(void* ws, size_t ws_bytes, int B, int N, int S, double T,
-               const double* x0, const double* theta, int theta_stride,
+CPDP_API int cpdp_solve(void* ws, size_t ws_bytes, int B, int N, int S, double T,
+               const double* x0, const double* theta, int theta_stride, const double* pdata,
                double tol, int max_iter, int rounds,
                double* X, double* U, double* Lam, int* status, int* iters,
                double* kkt_out, double* cost_out, void* stream) {
-    using namespace cpdp;
+    using namespace CPDP_NS;
     if (!ws || B <= 0 || N <= 0 || S <= 0 || !x0 || !theta || !X || !U || !Lam || !status || !iters) return -1;
     if (theta_stride != 0 && theta_stride != NP) return -2;
     WsLayout w = ws_carve((char*)ws, B, N, S);
     if (w.bytes > ws_bytes) return -3;
     SolveArgs a = w.sa;
     a.B = B; a.N = N; a.S = S; a.T = T; a.tol = tol; a.max_iter = max_iter;
-    a.x0 = x0; a.theta = theta; a.theta_stride = theta_stride;
+    if (NQ > 0 && !pdata) return -8;
+    a.x0 = x0; a.theta = theta; a.theta_stride = theta_stride; a.pdata = pdata;
     a.X = X; a.U = U; a.Lam = Lam; a.status = status; a.iters = iters;
     if (kkt_out) a.kkt = kkt_out;
     if (cost_out) a.J = cost_out;
@@ -94,7 +101,9 @@ int cpdp_solve(void* ws, size_t ws_bytes, int B, int N, int S, double T,
     CPDP_LAUNCH(k_solve_init, sms * 4, 256, 0, st, a);
     CPDP_LAUNCH(k_compact, 1, COMPACT_THREADS, 0, st, a);
     const int total_rounds = (rounds > 0) ? rounds : max_iter + 1;
+    g_last_rounds = 0;
     for (int it = 0; it < total_rounds; ++it) {
+        ++g_last_rounds;
         CPDP_LAUNCH(k_stage_adjoint, sms * 8, 128, 0, st, a);
         CPDP_LAUNCH(k_stage_hessian, sms * 4, HESS_THREADS, 0, st, a);
         CPDP_LAUNCH(k_newton_step, sms * 16, NEWTON_THREADS, 0, st, a);
@@ -110,13 +119,13 @@ int cpdp_solve(void* ws, size_t ws_bytes, int B, int N, int S, double T,
 
 // Auxiliary system + loss (COCSys.auxSysSolver, CPDP.py:301-381; loss closures QuadAlgorithm.py:616-639).
 // mode 0: backward Riccati sweep with RK45 (rtol_b, atol_b); mode 1: BDF emulation of the as-shipped reference.
-int cpdp_aux(void* ws, size_t ws_bytes, int B, int N, int S, double T,
-             const double* theta, int theta_stride,
+CPDP_API int cpdp_aux(void* ws, size_t ws_bytes, int B, int N, int S, double T,
+             const double* theta, int theta_stride, const double* pdata,
              const double* X, const double* U, const double* Lam, const int* solve_status,
              int mode, double rtol_b, double atol_b, double rtol_f, double atol_f,
              int W, int D, const int* sel_host, const double* taus, int taus_stride, const double* wp,
              double* Xa, double* Ua, double* loss, double* dtheta, int* aux_status, int* counters, void* stream) {
-    using namespace cpdp;
+    using namespace CPDP_NS;
     if (!ws || B <= 0 || N <= 0 || !theta || !X || !U || !Lam || !Xa || !Ua || !loss || !dtheta || !aux_status || !counters) return -1;
     if (theta_stride != 0 && theta_stride != NP) return -2;
     if (W < 0 || D < 0 || D > MAX_SEL || (W > 0 && (!taus || !wp || !sel_host))) return -4;
@@ -124,7 +133,8 @@ int cpdp_aux(void* ws, size_t ws_bytes, int B, int N, int S, double T,
     WsLayout w = ws_carve((char*)ws, B, N, S);
     if (w.bytes > ws_bytes) return -3;
     AuxArgs a;
-    a.B = B; a.N = N; a.T = T; a.theta = theta; a.theta_stride = theta_stride;
+    if (NQ > 0 && !pdata) return -8;
+    a.B = B; a.N = N; a.T = T; a.theta = theta; a.theta_stride = theta_stride; a.pdata = pdata;
     a.X = X; a.U = U; a.Lam = Lam;
     a.rtol_b = rtol_b; a.atol_b = atol_b; a.rtol_f = rtol_f; a.atol_f = atol_f;
     a.PW = w.PW; a.Xa = Xa; a.Ua = Ua;
@@ -147,8 +157,8 @@ int cpdp_aux(void* ws, size_t ws_bytes, int B, int N, int S, double T,
 }
 
 // Fixed-shape binary-tree sum over B rows of [loss | dL/dtheta] -> out[1+NP].  scratch: nextpow2(B)*(1+NP) doubles.
-int cpdp_reduce(const double* loss, const double* dtheta, int B, double* scratch, double* out, void* stream) {
-    using namespace cpdp;
+CPDP_API int cpdp_reduce(const double* loss, const double* dtheta, int B, double* scratch, double* out, void* stream) {
+    using namespace CPDP_NS;
     if (!loss || !dtheta || !out || !scratch || B <= 0) return -1;
     CPDP_LAUNCH(k_reduce_tree, 1, 256, 0, (cudaStream_t)stream, loss, dtheta, B, scratch, out);
     return CPDP_LAST_ERROR();

@@ -12,7 +12,7 @@
 #pragma once
 #include "cpdp_kernels.cuh"
 
-namespace cpdp {
+namespace CPDP_NS {
 
 constexpr int NT = NX * (NX + 1) / 2;          // packed upper triangle of P
 constexpr int NYR = NT + NX * NP;              // Riccati state
@@ -27,6 +27,7 @@ struct AuxArgs {
     int B, N;
     double T;
     const double* theta; int theta_stride;
+    const double* pdata;   // [B][NQ]
     const double* X; const double* U; const double* Lam;   // [B][N+1][.]
     double rtol_b, atol_b, rtol_f, atol_f;
     double* PW;            // [B][N+1][NYR]   packed Riccati nodes
@@ -120,7 +121,7 @@ struct AuxShared {
 };
 
 struct AuxProblem {
-    const double* X; const double* U; const double* Lam; const double* th;
+    const double* X; const double* U; const double* Lam; const double* th; const double* pd;
     const double* PW;          // node table (forward sweep)
     double dt; int N;
 };
@@ -132,7 +133,7 @@ CPDP_D bool pmp_at(const AuxProblem& p, double t, double* xul, double* M) {
     for (int i = 0; i < NX; ++i) xul[i] = interp_val(p.X[(size_t)lo * NX + i], p.X[(size_t)(lo + 1) * NX + i], xlo, xhi, t);
     for (int i = 0; i < NU; ++i) xul[NX + i] = interp_val(p.U[(size_t)lo * NU + i], p.U[(size_t)(lo + 1) * NU + i], xlo, xhi, t);
     for (int i = 0; i < NX; ++i) xul[NX + NU + i] = interp_val(p.Lam[(size_t)lo * NX + i], p.Lam[(size_t)(lo + 1) * NX + i], xlo, xhi, t);
-    Model::pmp(xul, xul + NX, xul + NX + NU, p.th, M);
+    Model::pmp(xul, xul + NX, xul + NX + NU, p.th, p.pd, M);
     return inv_small<NU>(M + Model::PMP_HUU, M + Model::PMP_SIZE);
 }
 
@@ -467,7 +468,12 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
     CPDP_SHARED int s_ti[NT], s_tj[NT];
     CPDP_SHARED double s_hxx[NX * NX], s_hxe[NX * NP];
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    if (a.solve_status && a.solve_status[b] != ST_CONVERGED) { if (tid == 0) a.aux_status[b] = 3; return; }
+    // The reference never looks at IPOPT's return status (CPDP.py:183); here trajectories that are not a solution
+    // at all (NaN / still iterating) are skipped and flagged, max-iter / line-search exits are integrated as they are.
+    if (a.solve_status && (a.solve_status[b] == ST_NUMERIC || a.solve_status[b] == ST_RUNNING)) {
+        if (tid == 0) a.aux_status[b] = 3;
+        return;
+    }
     double* ptr = smem;
     AuxShared s;
     aux_shared_common(s, ptr, s_ti, s_tj);
@@ -476,7 +482,7 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
     const int N = a.N;
     AuxProblem p;
     p.X = a.X + (size_t)b * (N + 1) * NX; p.U = a.U + (size_t)b * (N + 1) * NU; p.Lam = a.Lam + (size_t)b * (N + 1) * NX;
-    p.th = a.theta + (size_t)b * a.theta_stride; p.PW = nullptr; p.dt = a.T / N; p.N = N;
+    p.th = a.theta + (size_t)b * a.theta_stride; p.pd = a.pdata + (size_t)b * NQ; p.PW = nullptr; p.dt = a.T / N; p.N = N;
     double* PW = a.PW + (size_t)b * (N + 1) * NYR;
     if (tid == 0) {
         // terminal condition at opt_sol(time_grid[-1]) (CPDP.py:327-331); interp1d at the last node returns
@@ -485,7 +491,7 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
         double xT[NX];
         const int lo = interp_lo(tN, p.dt, N);
         for (int i = 0; i < NX; ++i) xT[i] = interp_val(p.X[(size_t)lo * NX + i], p.X[(size_t)(lo + 1) * NX + i], p.dt * lo, p.dt * (lo + 1), tN);
-        Model::term2(xT, p.th, s_hxx, s_hxe);
+        Model::term2(xT, p.th, p.pd, s_hxx, s_hxe);
     }
     __syncthreads();
     for (int q = tid; q < NYR; q += nt) {
@@ -526,7 +532,7 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_aux_forward(AuxArgs a) {
     const int N = a.N;
     AuxProblem p;
     p.X = a.X + (size_t)b * (N + 1) * NX; p.U = a.U + (size_t)b * (N + 1) * NU; p.Lam = a.Lam + (size_t)b * (N + 1) * NX;
-    p.th = a.theta + (size_t)b * a.theta_stride; p.PW = a.PW + (size_t)b * (N + 1) * NYR; p.dt = a.T / N; p.N = N;
+    p.th = a.theta + (size_t)b * a.theta_stride; p.pd = a.pdata + (size_t)b * NQ; p.PW = a.PW + (size_t)b * (N + 1) * NYR; p.dt = a.T / N; p.N = N;
     double* Xa = a.Xa + (size_t)b * (N + 1) * NYF;
     double* Ua = a.Ua + (size_t)b * (N + 1) * NU * NP;
     for (int q = tid; q < NYF; q += nt) { y[q] = 0.0; Xa[q] = 0.0; }
@@ -600,4 +606,4 @@ CPDP_GLOBAL void __launch_bounds__(256) k_reduce_tree(const double* loss, const 
     for (int c = tid; c < C; c += nt) out[c] = scratch[c];
 }
 
-}  // namespace cpdp
+}  // namespace CPDP_NS

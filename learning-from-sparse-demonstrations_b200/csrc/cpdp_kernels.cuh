@@ -11,12 +11,13 @@
 #pragma once
 #include "cpdp_port.h"
 
-namespace cpdp {
+namespace CPDP_NS {
 
 constexpr int NX = Model::NX;
 constexpr int NU = Model::NU;
 constexpr int NP = Model::NP;
 constexpr int NZ = NX + NU;
+constexpr int NQ = Model::NQ;          // per-problem constants (not learnable)
 
 enum Status { ST_RUNNING = 0, ST_CONVERGED = 1, ST_MAXITER = 2, ST_LINESEARCH = 3, ST_NUMERIC = 4 };
 
@@ -31,6 +32,7 @@ struct SolveArgs {
     const double* x0;            // [B][NX]
     const double* theta;         // [B or 1][NP]
     int theta_stride;            // NP or 0
+    const double* pdata;         // [B][NQ] per-problem constants (may be null if NQ == 0)
     double* X;                   // [B][N+1][NX]   NLP states (in/out)
     double* U;                   // [B][N+1][NU]   NLP controls, row N := row N-1 on exit
     double* Lam;                 // [B][N+1][NX]   multipliers of [x0-X0, F_k-X_{k+1}]
@@ -61,32 +63,33 @@ struct SolveArgs {
 };
 
 CPDP_HD const double* theta_of(const SolveArgs& a, int b) { return a.theta + (size_t)b * a.theta_stride; }
+CPDP_HD const double* pdata_of(const SolveArgs& a, int b) { return a.pdata + (size_t)b * NQ; }
 
 // One classical RK4 step of (f, c) with frozen control (CPDP.py:117-123).
-CPDP_HD void rk4_step(const double* x, const double* u, const double* th, double DT, double* xn, double& q) {
+CPDP_HD void rk4_step(const double* x, const double* u, const double* th, const double* pd, double DT, double* xn, double& q) {
     double k[NX], xt[NX], c;
-    Model::fc(x, u, th, k, c);
+    Model::fc(x, u, th, pd, k, c);
     double qa = c;
     for (int i = 0; i < NX; ++i) { xn[i] = x[i] + DT / 6 * k[i]; xt[i] = x[i] + DT / 2 * k[i]; }
-    Model::fc(xt, u, th, k, c);
+    Model::fc(xt, u, th, pd, k, c);
     qa += 2 * c;
     for (int i = 0; i < NX; ++i) { xn[i] += DT / 3 * k[i]; xt[i] = x[i] + DT / 2 * k[i]; }
-    Model::fc(xt, u, th, k, c);
+    Model::fc(xt, u, th, pd, k, c);
     qa += 2 * c;
     for (int i = 0; i < NX; ++i) { xn[i] += DT / 3 * k[i]; xt[i] = x[i] + DT * k[i]; }
-    Model::fc(xt, u, th, k, c);
+    Model::fc(xt, u, th, pd, k, c);
     qa += c;
     for (int i = 0; i < NX; ++i) xn[i] += DT / 6 * k[i];
     q += DT / 6 * qa;
 }
 
 // S RK4 steps over one grid interval: x -> x_end, q = integral of the path cost.
-CPDP_HD void rk4_interval(const double* x, const double* u, const double* th, double DT, int S, double* xe, double& q) {
+CPDP_HD void rk4_interval(const double* x, const double* u, const double* th, const double* pd, double DT, int S, double* xe, double& q) {
     double xa[NX], xb[NX];
     for (int i = 0; i < NX; ++i) xa[i] = x[i];
     q = 0.0;
     for (int s = 0; s < S; ++s) {
-        rk4_step(xa, u, th, DT, xb, q);
+        rk4_step(xa, u, th, pd, DT, xb, q);
         for (int i = 0; i < NX; ++i) xa[i] = xb[i];
     }
     for (int i = 0; i < NX; ++i) xe[i] = xa[i];
@@ -109,6 +112,7 @@ CPDP_D void stage_adjoint_item(const SolveArgs& a, int b, int k) {
     const int idx = b * a.N + k;
     const double DT = a.T / a.N / a.S;
     const double* th = theta_of(a, b);
+    const double* pd = pdata_of(a, b);
     double x[NX], u[NU];
     {
         const double* xk = a.X + ((size_t)b * (a.N + 1) + k) * NX;
@@ -124,16 +128,16 @@ CPDP_D void stage_adjoint_item(const SolveArgs& a, int b, int k) {
         for (int s = 0; s < a.S; ++s) {
             double* st = xs + (size_t)s * 4 * NX;
             for (int i = 0; i < NX; ++i) st[i] = x[i];
-            Model::fc(x, u, th, kk, c);
+            Model::fc(x, u, th, pd, kk, c);
             double qa = c;
             for (int i = 0; i < NX; ++i) { xn[i] = x[i] + DT / 6 * kk[i]; xt[i] = x[i] + DT / 2 * kk[i]; st[NX + i] = xt[i]; }
-            Model::fc(xt, u, th, kk, c);
+            Model::fc(xt, u, th, pd, kk, c);
             qa += 2 * c;
             for (int i = 0; i < NX; ++i) { xn[i] += DT / 3 * kk[i]; xt[i] = x[i] + DT / 2 * kk[i]; st[2 * NX + i] = xt[i]; }
-            Model::fc(xt, u, th, kk, c);
+            Model::fc(xt, u, th, pd, kk, c);
             qa += 2 * c;
             for (int i = 0; i < NX; ++i) { xn[i] += DT / 3 * kk[i]; xt[i] = x[i] + DT * kk[i]; st[3 * NX + i] = xt[i]; }
-            Model::fc(xt, u, th, kk, c);
+            Model::fc(xt, u, th, pd, kk, c);
             qa += c;
             for (int i = 0; i < NX; ++i) x[i] = xn[i] + DT / 6 * kk[i];
             q += DT / 6 * qa;
@@ -164,7 +168,7 @@ CPDP_D void stage_adjoint_item(const SolveArgs& a, int b, int k) {
             for (int i = 0; i < NX; ++i) kap[i] = bco[st] * DT * adj[i] + cnext * xi[i];
             double* mp = mus + ((size_t)s * 4 + st) * NX;
             for (int i = 0; i < NX; ++i) mp[i] = kap[i];
-            Model::hgrad(xst, u, th, kap, bco[st] * DT, xi, g_u);
+            Model::hgrad(xst, u, th, pd, kap, bco[st] * DT, xi, g_u);
             for (int i = 0; i < NX; ++i) ax[i] += xi[i];
             for (int i = 0; i < NU; ++i) gu[i] += g_u[i];
         }
@@ -188,6 +192,7 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS) k_stage_hessian(SolveArgs a) {
     CPDP_SHARED double s_mu[KPC][NX];
     CPDP_SHARED double s_u[KPC][NU];
     CPDP_SHARED double s_th[KPC][NP];
+    CPDP_SHARED double s_pd[KPC][NQ > 0 ? NQ : 1];
     CPDP_SHARED double s_S[KPC][NZ][NX];
     CPDP_SHARED int s_gi[KPC];                 // global interval index b*N+k of each slot, -1 if none
     const int tid = threadIdx.x;
@@ -205,13 +210,14 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS) k_stage_hessian(SolveArgs a) {
             s_gi[t] = (li < total) ? a.act[li / a.N] * a.N + li % a.N : -1;
         }
         __syncthreads();
-        for (int t = tid; t < KPC * (NU + NP); t += HESS_THREADS) {
-            const int q = t / (NU + NP), e = t % (NU + NP);
+        for (int t = tid; t < KPC * (NU + NP + NQ); t += HESS_THREADS) {
+            const int q = t / (NU + NP + NQ), e = t % (NU + NP + NQ);
             const int gi = s_gi[q];
             if (gi >= 0) {
                 const int b = gi / a.N, k = gi % a.N;
                 if (e < NU) s_u[q][e] = a.U[((size_t)b * (a.N + 1) + k) * NU + e];
-                else s_th[q][e - NU] = theta_of(a, b)[e - NU];
+                else if (e < NU + NP) s_th[q][e - NU] = theta_of(a, b)[e - NU];
+                else s_pd[q][e - NU - NP] = pdata_of(a, b)[e - NU - NP];
             }
         }
         const bool mine = (kk < KPC) && (s_gi[kk < KPC ? kk : 0] >= 0);
@@ -239,7 +245,7 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS) k_stage_hessian(SolveArgs a) {
                 if (mine) {
                     const double ca = aco[st] * DT;
                     for (int i = 0; i < NX; ++i) dX[i] = Sx[i] + ca * df[i];
-                    Model::dir(s_x[kk], s_u[kk], s_th[kk], s_mu[kk], bco[st] * DT, dX, du, df, hz);
+                    Model::dir(s_x[kk], s_u[kk], s_th[kk], s_pd[kk], s_mu[kk], bco[st] * DT, dX, du, df, hz);
                     for (int i = 0; i < NX; ++i) s_S[kk][j][i] = dX[i];
                 }
                 __syncthreads();
@@ -330,6 +336,7 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
     const int N = a.N;
     const double DT = a.T / a.N / a.S;
     const double* th = theta_of(a, b);
+    const double* pd = pdata_of(a, b);
     double* X = a.X + (size_t)b * (N + 1) * NX;
     double* U = a.U + (size_t)b * (N + 1) * NU;
     double* Lam = a.Lam + (size_t)b * (N + 1) * NX;
@@ -352,8 +359,8 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
     // ---- terminal cost derivatives, defect of the initial condition
     if (tid == 0) {
         double h;
-        Model::term(X + (size_t)N * NX, th, h, s_hx);
-        Model::term2(X + (size_t)N * NX, th, s_hxx, s_hxe);
+        Model::term(X + (size_t)N * NX, th, pd, h, s_hx);
+        Model::term2(X + (size_t)N * NX, th, pd, s_hxx, s_hxe);
         s_h = h;
     }
     for (int i = tid; i < NX; i += nt) dfc[i] = a.x0[(size_t)b * NX + i] - X[i];
@@ -550,13 +557,13 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
             if (k < N) {
                 double uk[NU], xe[NX], q;
                 for (int i = 0; i < NU; ++i) uk[i] = U[(size_t)k * NU + i] + alpha * dU[(size_t)k * NU + i];
-                rk4_interval(xk, uk, th, DT, a.S, xe, q);
+                rk4_interval(xk, uk, th, pd, DT, a.S, xe, q);
                 Jt += q;
                 for (int i = 0; i < NX; ++i)
                     gt += fabs(xe[i] - (X[(size_t)(k + 1) * NX + i] + alpha * dX[(size_t)(k + 1) * NX + i]));
             } else {
                 double h, hx[NX];
-                Model::term(xk, th, h, hx);
+                Model::term(xk, th, pd, h, hx);
                 Jt += h;
             }
             if (k == 0) for (int i = 0; i < NX; ++i) gt += fabs(a.x0[(size_t)b * NX + i] - xk[i]);
@@ -619,4 +626,4 @@ CPDP_GLOBAL void __launch_bounds__(COMPACT_THREADS) k_compact(SolveArgs a) {
     for (int i = lo; i < hi; ++i) if (a.status[i] == ST_RUNNING) a.act[o++] = i;
 }
 
-}  // namespace cpdp
+}  // namespace CPDP_NS

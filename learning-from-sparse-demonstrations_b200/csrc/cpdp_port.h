@@ -4,6 +4,13 @@
 // host branch exists only so that kernel logic can be checked in a container that has no GPU.
 #pragma once
 
+// Every model library gets its own C++ namespace (-DCPDP_NS=cpdp_<model>) and hidden visibility, so that several
+// model libraries can live in one process without their kernels' host stubs or inline statics being merged.
+#ifndef CPDP_NS
+#define CPDP_NS cpdp
+#endif
+#define CPDP_API __attribute__((visibility("default")))
+
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define CPDP_HD __host__ __device__ __forceinline__

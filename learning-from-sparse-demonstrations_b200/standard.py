@@ -1,0 +1,89 @@
+"""The optimal-control systems of the reference's example scripts, built exactly as the scripts build them
+(time-warping wrapper: dyn = beta*f, path = beta*c, final cost unscaled, theta = [beta; cost_auxvar]).
+Each function returns a COCSys with a stable library name so that ``__graft_entry__.build()`` can prebuild it.
+"""
+import math
+
+from . import JinEnv
+from .CPDP import COCSys
+from .sx import SX, vertcat
+
+
+def _wrap(env, name, n_grid):
+    """/root/reference/Examples/pendulum_groundtruth.py:21-30 (identical in every example)."""
+    oc = COCSys(name)
+    beta = SX.sym('beta')
+    oc.setAuxvarVariable(vertcat(beta, env.cost_auxvar))
+    oc.setStateVariable(env.X)
+    oc.setControlVariable(env.U)
+    oc.setDyn(beta * env.f)
+    oc.setPathCost(beta * env.path_cost)
+    oc.setFinalCost(env.final_cost)
+    oc.setIntegrator(n_grid=n_grid)
+    oc.env = env
+    oc.lib_name = name
+    return oc
+
+
+def pendulum_oc(n_grid=10):
+    """Examples/pendulum_groundtruth.py:16-18 ; observed: q (x[0])."""
+    env = JinEnv.SinglePendulum()
+    env.initDyn(l=1, m=1, damping_ratio=0.1)
+    env.initCost(wu=.01)
+    oc = _wrap(env, "pendulum", n_grid)
+    oc.sel = [0]
+    return oc
+
+
+def robotarm_oc(n_grid=30):
+    """Examples/robotarm_random.py:14-29 ; observed: q1, q2."""
+    env = JinEnv.RobotArm()
+    env.initDyn(l1=1, m1=1, l2=1, m2=1, g=0)
+    env.initCost_Polynomial(wu=.5)
+    oc = _wrap(env, "robotarm", n_grid)
+    oc.sel = [0, 1]
+    return oc
+
+
+def rocket_oc(n_grid=15):
+    """Examples/rocket_groundtruth.py:15-30 ; observed: position and quaternion."""
+    env = JinEnv.Rocket()
+    env.initDyn(Jx=1, Jy=1, Jz=1, mass=1, l=1)
+    env.initCost2(wthrust=0.1)
+    oc = _wrap(env, "rocket", n_grid)
+    oc.sel = [0, 1, 2, 6, 7, 8, 9]
+    return oc
+
+
+def quadrotor_oc(n_grid=25, goal_position=None):
+    """lib/QuadAlgorithm.py:74-104 with QuadPara(1,1,1, mass=1, l=1, c=0.02) (Examples/quad_example.py:26).
+    With goal_position=None the goal position is per-problem data (3 constants), which is what the batched
+    benchmark needs; a numeric goal is baked into the model like the reference does."""
+    env = JinEnv.Quadrotor()
+    env.initDyn(Jx=1.0, Jy=1.0, Jz=1.0, mass=1.0, l=1.0, c=0.02)
+    goal = JinEnv.QuadStates()
+    pvar = None
+    if goal_position is None:
+        pvar = vertcat(SX.sym('goal_x'), SX.sym('goal_y'), SX.sym('goal_z'))
+        goal.position = pvar
+        name = "quadrotor"
+    else:
+        goal.position = list(goal_position)
+        name = "quadrotor_fixedgoal"
+    env.initCost_Polynomial(goal, w_thrust=0.1)
+    oc = _wrap(env, name, n_grid)
+    if pvar is not None:
+        oc.setProblemVariable(pvar)
+    oc.sel = [0, 1, 2]
+    return oc
+
+
+STANDARD = {"pendulum": pendulum_oc, "robotarm": robotarm_oc, "rocket": rocket_oc, "quadrotor": quadrotor_oc}
+
+
+def build_all(verbose=False):
+    libs = {}
+    for name, fn in STANDARD.items():
+        oc = fn()
+        libs[name] = oc.build(name=oc.lib_name, verbose=verbose).path
+    return libs

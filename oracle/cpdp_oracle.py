@@ -40,11 +40,12 @@ class _Fns:
         self.model = model
         n, m, r = model.n, model.m, model.r
         x, u, th = model.x, model.u, model.theta
+        pd = list(getattr(model, 'pdata', []))
         z = x + u
         mu = [sp.Symbol('mu%d' % i, real=True) for i in range(n)]
         wc = sp.Symbol('wc', real=True)
         f, c, h = model.dyn, model.path, model.final
-        args = [x, u, th]
+        args = [x, u, th, pd]
 
         def lam(a, outs):
             flat = sp.Matrix([e for o in outs for e in (list(o) if isinstance(o, sp.MatrixBase) else [o])])
@@ -77,11 +78,11 @@ class _Fns:
         Hp = c + (sp.Matrix(lm).T * f)[0, 0]
         Hx = sp.Matrix([Hp]).jacobian(x)
         Hu = sp.Matrix([Hp]).jacobian(u)
-        self.pmp = lam([x, u, lm, th], [f.jacobian(x), f.jacobian(u), f.jacobian(th),
+        self.pmp = lam([x, u, lm, th, pd], [f.jacobian(x), f.jacobian(u), f.jacobian(th),
                                         Hx.jacobian(x), Hx.jacobian(u), Hx.jacobian(th),
                                         Hu.jacobian(u), Hu.jacobian(th)])
         hx = sp.Matrix([h]).jacobian(x)
-        self.term = lam([x, th], [h, hx, hx.jacobian(x), hx.jacobian(th)])
+        self.term = lam([x, th, pd], [h, hx, hx.jacobian(x), hx.jacobian(th)])
 
 
 class Oracle:
@@ -90,6 +91,7 @@ class Oracle:
         self.n, self.m, self.r = model.n, model.m, model.r
         self.N, self.S = int(n_grid), int(steps_per_grid)
         self.fn = _Fns(model)
+        self.pd = np.zeros(len(getattr(model, 'pdata', [])))   # per-problem constants (e.g. goal position)
 
     # -----------------------------------------------------------------------------------------
     # RK4 interval map (CPDP.py:111-124)
@@ -100,10 +102,10 @@ class Oracle:
         Q = 0.0
         fc = self.fn.fc
         for _ in range(self.S):
-            k1, q1 = fc(X, u, th)
-            k2, q2 = fc(X + DT / 2 * k1, u, th)
-            k3, q3 = fc(X + DT / 2 * k2, u, th)
-            k4, q4 = fc(X + DT * k3, u, th)
+            k1, q1 = fc(X, u, th, self.pd)
+            k2, q2 = fc(X + DT / 2 * k1, u, th, self.pd)
+            k3, q3 = fc(X + DT / 2 * k2, u, th, self.pd)
+            k4, q4 = fc(X + DT * k3, u, th, self.pd)
             X = X + DT / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
             Q = Q + DT / 6 * (q1 + 2 * q2 + 2 * q3 + q4)
         return X, Q
@@ -130,7 +132,7 @@ class Oracle:
             for s in range(4):
                 xs = X if s == 0 else X + aco[s] * DT * kprev
                 Ss = Sx if s == 0 else Sx + aco[s] * DT * dkprev
-                f, c, fz, cz = self.fn.stage1(xs, u, th)
+                f, c, fz, cz = self.fn.stage1(xs, u, th, self.pd)
                 Sz = np.vstack([Ss, E])
                 dk = fz @ Sz
                 stages.append((xs, fz, cz.ravel(), Sz))
@@ -155,7 +157,7 @@ class Oracle:
                     kap = kap + aco[s + 1] * DT * kap_next_xi
                 w = bco[s] * DT
                 xs, fz, cz, Sz = stages[s]
-                Hzz, = self.fn.stage2(xs, u, th, kap, w)
+                Hzz, = self.fn.stage2(xs, u, th, self.pd, kap, w)
                 H += Sz.T @ Hzz @ Sz
                 xi = fz[:, :n].T @ kap + w * cz[:n]
                 ax += xi
@@ -188,7 +190,7 @@ class Oracle:
                 xe, q = self.interval(wv[ox(k):ox(k) + n], wv[ou(k):ou(k) + m], th, DT)
                 J += q
                 g[(k + 1) * n:(k + 2) * n] = xe - wv[ox(k + 1):ox(k + 1) + n]
-            J += self.fn.term(wv[ox(N):ox(N) + n], th)[0]
+            J += self.fn.term(wv[ox(N):ox(N) + n], th, self.pd)[0]
             return J, g
 
         nu = 0.0
@@ -213,7 +215,7 @@ class Oracle:
                 Ag[(k + 1) * n:(k + 2) * n, ox(k):ox(k) + n] = A
                 Ag[(k + 1) * n:(k + 2) * n, ou(k):ou(k) + m] = B
                 Ag[(k + 1) * n:(k + 2) * n, ox(k + 1):ox(k + 1) + n] = -np.eye(n)
-            hv, hx, hxx, _ = self.fn.term(w[ox(N):ox(N) + n], th)
+            hv, hx, hxx, _ = self.fn.term(w[ox(N):ox(N) + n], th, self.pd)
             J += hv
             gradJ[ox(N):ox(N) + n] += hx.ravel()
             W[ox(N):ox(N) + n, ox(N):ox(N) + n] += hxx
@@ -254,8 +256,12 @@ class Oracle:
             Dphi = gradJ @ d - nu * g1
             alpha = 1.0
             while True:
-                Jt, gt = evaluate(w + alpha * d)
-                phit = Jt + nu * np.abs(gt).sum()
+                try:
+                    with np.errstate(all='ignore'):
+                        Jt, gt = evaluate(w + alpha * d)
+                    phit = Jt + nu * np.abs(gt).sum()
+                except (ValueError, OverflowError, FloatingPointError):   # e.g. math.cos(inf) at a wild trial point
+                    phit = np.inf
                 if np.isfinite(phit) and phit <= phi0 + 1e-4 * alpha * Dphi:
                     break
                 alpha *= 0.5
@@ -285,7 +291,7 @@ class Oracle:
     # auxiliary system (CPDP.py:253-381)
     # -----------------------------------------------------------------------------------------
     def _coeffs(self, x, u, lam, th):
-        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue = self.fn.pmp(x, u, lam, th)
+        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue = self.fn.pmp(x, u, lam, th, self.pd)
         invHuu = np.linalg.inv(Huu)
         return fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu
 
@@ -337,7 +343,7 @@ class Oracle:
             return np.concatenate((Pd.flatten(), Wd.flatten()))
 
         xT = opt_sol(float(time_grid[-1]))[:n]
-        _, _, hxx, hxe = self.fn.term(xT, th)
+        _, _, hxx, hxe = self.fn.term(xT, th, self.pd)
         PW = np.zeros((N + 1, n * n + n * r))
         PW[-1, :] = np.concatenate((hxx.flatten(), hxe.flatten()))
         for k in range(N, 0, -1):

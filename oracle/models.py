@@ -23,7 +23,7 @@ class OracleModel:
     """x (n), u (m), theta (r) symbols and the three expressions dyn (n), path (scalar), final (scalar).
     ``sel`` lists the state indices observed by the loss closure of the matching example."""
 
-    def __init__(self, name, x, u, theta, dyn, path, final, sel):
+    def __init__(self, name, x, u, theta, dyn, path, final, sel, pdata=()):
         self.name = name
         self.x, self.u, self.theta = list(x), list(u), list(theta)
         self.n, self.m, self.r = len(self.x), len(self.u), len(self.theta)
@@ -31,6 +31,7 @@ class OracleModel:
         self.path = sp.sympify(path)
         self.final = sp.sympify(final)
         self.sel = list(sel)
+        self.pdata = list(pdata)      # per-problem constants (not learnable), e.g. a symbolic goal position
 
 
 def _syms(names):
@@ -93,11 +94,15 @@ def robotarm(l1=1.0, m1=1.0, l2=1.0, m2=1.0, g=0.0, wu=0.5):
                        beta * f, beta * c, h, sel=[0, 1])
 
 
-def quadrotor(goal_r=(0., 0., 0.), goal_v=(0., 0., 0.), goal_q=(1., 0., 0., 0.), goal_w=(0., 0., 0.),
+def quadrotor(goal_r=None, goal_v=(0., 0., 0.), goal_q=(1., 0., 0., 0.), goal_w=(0., 0., 0.),
               J=(1.0, 1.0, 1.0), mass=1.0, l=1.0, c=0.02, w_thrust=0.1):
     r = _syms('rx ry rz'); v = _syms('vx vy vz'); q = _syms('q0 q1 q2 q3'); w = _syms('wx wy wz')
     f_ = _syms('f1 f2 f3 f4')
     beta, wxs, wx_, wys, wy_, wzs, wz_ = _syms('beta w_xsq w_x w_ysq w_y w_zsq w_z')
+    pdata = []
+    if goal_r is None:            # symbolic goal position -> per-problem data
+        pdata = _syms('goal_x goal_y goal_z')
+        goal_r = pdata
     thrust = sp.Matrix([0, 0, sum(f_)])
     Mb = [(-f_[1] + f_[3]) * l / 2, (-f_[0] + f_[2]) * l / 2, (f_[0] - f_[1] + f_[2] - f_[3]) * c]
     C_I_B = _dcm(q).T
@@ -109,7 +114,7 @@ def quadrotor(goal_r=(0., 0., 0.), goal_v=(0., 0., 0.), goal_q=(1., 0., 0., 0.),
     h = (1 * sum((a - b) ** 2 for a, b in zip(r, goal_r)) + 11 * sum((a - b) ** 2 for a, b in zip(v, goal_v))
          + 100 * att + 10 * sum((a - b) ** 2 for a, b in zip(w, goal_w)))
     return OracleModel('quadrotor', r + v + q + w, f_, [beta, wxs, wx_, wys, wy_, wzs, wz_],
-                       beta * f, beta * path, h, sel=[0, 1, 2])
+                       beta * f, beta * path, h, sel=[0, 1, 2], pdata=pdata)
 
 
 def rocket(J=(1.0, 1.0, 1.0), mass=1.0, l=1.0, wthrust=0.1):

@@ -17,7 +17,7 @@
 
 thread_local cpdp_emu_dim3 threadIdx;
 cpdp_emu_dim3 blockIdx, blockDim, gridDim;
-double* cpdp_emu_dyn_smem = nullptr;
+double* cpdp_emu_dyn_smem = nullptr;   // (hidden visibility: private to this library)
 static std::barrier<>* g_bar = nullptr;
 void cpdp_emu_syncthreads() { g_bar->arrive_and_wait(); }
 
@@ -43,7 +43,7 @@ static void emu_launch(F kernel, int grid, int block, size_t smem, Args... args)
     }
 }
 
-#define CPDP_LAUNCH(kernel, grid, block, smem, stream, ...) emu_launch(cpdp::kernel, grid, block, smem, __VA_ARGS__)
+#define CPDP_LAUNCH(kernel, grid, block, smem, stream, ...) emu_launch(CPDP_NS::kernel, grid, block, smem, __VA_ARGS__)
 #define CPDP_READ_INT(dst, src, stream) (dst) = *(src)
 #define CPDP_NUM_SMS() 1
 #define CPDP_PREPARE_SMEM(kernel, bytes) (void)0

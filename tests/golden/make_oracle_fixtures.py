@@ -1,0 +1,87 @@
+"""Generates parity fixtures with the CPU oracle (oracle/cpdp_oracle.py), which is itself pinned against the
+reference's stored run (tests/test_oracle_kat.py).  Run from the repo root:  python tests/golden/make_oracle_fixtures.py
+Output: tests/golden/oracle_<case>.npz with the converged trajectory and the loss / gradient under
+  asshipped : BDF backward (scipy defaults) + RK45 forward (defaults)   = what the reference's COCSys computes
+  rk45      : RK45 backward (defaults) + RK45 forward (defaults)
+  tight     : rtol 1e-10 / atol 1e-12 both sweeps
+"""
+import os
+import sys
+import time
+from multiprocessing import Pool
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import lfsd_b200  # noqa: E402,F401
+from lfsd_b200 import synthetic  # noqa: E402
+from oracle import models  # noqa: E402
+from oracle.cpdp_oracle import Oracle, TIGHT  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def run_problem(args):
+    kind, n_grid, x0, T, theta, pd, taus, wp = args
+    mdl = getattr(models, kind)()
+    orc = Oracle(mdl, n_grid=n_grid)
+    if pd is not None:
+        orc.pd = np.asarray(pd, dtype=float)
+    tg, X, U, Lam, info = orc.solve(x0, T, theta, return_info=True)
+    out = dict(X=X, U=U, Lam=Lam, iters=info['iters'], J=info['J'], kkt=info['kkt'])
+    for tag, back, fwd in (('asshipped', {'method': 'BDF'}, {}), ('rk45', {}, {}), ('tight', TIGHT, TIGHT)):
+        Xa, Ua, PW, cnt = orc.aux(tg, X, U, Lam, theta, back=back, fwd=fwd, return_counts=True)
+        loss, dl = orc.loss_grad(taus, wp, tg, X, Xa)
+        out['Xa_' + tag] = Xa; out['Ua_' + tag] = Ua; out['loss_' + tag] = loss; out['dl_' + tag] = dl
+        out['cnt_' + tag] = np.array([cnt['back_rhs'], cnt['fwd_rhs']])
+        if tag == 'asshipped':
+            out['PW_asshipped'] = PW
+    return out
+
+
+def stack(results):
+    return {k: np.stack([np.asarray(r[k]) for r in results]) for k in results[0]}
+
+
+def main():
+    t0 = time.time()
+    jobs = {}
+    # pendulum, as in Examples/pendulum_groundtruth.py: waypoints from theta*=[2,1,1] at grid idx [1,3,6,7,9]
+    mdl = models.pendulum(); orc = Oracle(mdl, n_grid=10)
+    tg, Xs, _, _ = orc.solve([0.0, 0.0], 1.0, [2.0, 1.0, 1.0])
+    idx = [1, 3, 6, 7, 9]
+    p_taus, p_wp = tg[idx], Xs[idx, 0:1]
+    jobs['pendulum'] = [('pendulum', 10, np.zeros(2), 1.0, np.array(th), None, p_taus, p_wp)
+                        for th in ([1.0, 0.5, 1.5], [2.0, 1.0, 1.0], [1.3, 0.8, 1.2])]
+    ab = synthetic.robotarm_batch(4)
+    jobs['robotarm'] = [('robotarm', 30, ab['x0'][b], 1.0, ab['theta'][b], None, ab['taus'], ab['wp'][b]) for b in range(4)]
+    jobs['robotarm'][0] = ('robotarm', 30, ab['x0'][0], 1.0, np.array([5.0, 1, 1, 1, 1]), None, ab['taus'], ab['wp'][0])
+    rb = synthetic.rocket_batch(2)
+    mdl = models.rocket(); orc = Oracle(mdl, n_grid=15)
+    rjobs = []
+    for b in range(2):
+        tg, Xs, _, _ = orc.solve(rb['x0'][b], 3.0, rb['theta_true'])
+        rjobs.append(('rocket', 15, rb['x0'][b], 3.0, rb['theta0'], None, tg[rb['tau_idx']], Xs[rb['tau_idx']][:, rb['sel']]))
+    jobs['rocket'] = rjobs
+    qb = synthetic.quad_batch(4096)
+    jobs['quad50'] = [('quadrotor', 50, qb['x0'][b], 1.0, qb['theta'], qb['goal'][b], qb['taus'], qb['wp'][b]) for b in range(6)]
+    g = np.load(os.path.join(HERE, 'quad_run.npz'))
+    jobs['quadkat'] = [('quadrotor', 25, g['ini_state'], 1.0, g['parameter_trace'][0], g['goal_position'], g['time_grid'], g['waypoints'])]
+    flat = [(name, j) for name, lst in jobs.items() for j in lst]
+    with Pool(min(8, os.cpu_count())) as pool:
+        res = pool.map(run_problem, [j for _, j in flat])
+    for name in jobs:
+        rs = [r for (nm, _), r in zip(flat, res) if nm == name]
+        js = jobs[name]
+        d = stack(rs)
+        d.update(x0=np.stack([j[2] for j in js]), theta=np.stack([j[4] for j in js]), T=js[0][3], n_grid=js[0][1],
+                 taus=np.stack([j[6] for j in js]), wp=np.stack([j[7] for j in js]))
+        if js[0][5] is not None:
+            d['pdata'] = np.stack([j[5] for j in js])
+        np.savez_compressed(os.path.join(HERE, 'oracle_%s.npz' % name), **d)
+        print(name, 'iters', d['iters'], 'loss', d['loss_asshipped'], 'time %.0fs' % (time.time() - t0))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,71 @@
+"""Pins the CPU oracle against the reference's only stored outputs (KATs K1-K5).
+tests/golden/quad_run.npz is a verbatim extract of /root/reference/data/uav_results_random_20210308113016.mat."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import models
+from oracle.cpdp_oracle import Oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def run():
+    return np.load(os.path.join(HERE, "golden", "quad_run.npz"))
+
+
+@pytest.fixture(scope="module")
+def orc(run):
+    o = Oracle(models.quadrotor(), n_grid=int(run["n_grid"]), steps_per_grid=int(run["steps_per_grid"]))
+    o.pd = run["goal_position"].astype(float)
+    return o
+
+
+def test_k1_rollout(run, orc):
+    """RK4(S=4) applied to stored node states/controls reproduces the next stored node (<=1e-11)."""
+    th = run["parameter_trace"][-1]
+    X, U = run["opt_state_traj"], run["opt_control_traj"]
+    DT = 1.0 / 25 / 4
+    for k in range(25):
+        xe, _ = orc.interval(X[4 * k], U[4 * k], th, DT)
+        assert np.abs(xe - X[4 * k + 4]).max() < 1e-11
+    # rows between nodes are linear interpolation; last control row copies the previous node (CPDP.py:191)
+    for k in range(25):
+        for j in range(1, 4):
+            lin = X[4 * k] + (X[4 * k + 4] - X[4 * k]) * (j / 4.0)
+            assert np.abs(lin - X[4 * k + j]).max() < 1e-13
+    assert np.array_equal(U[100], U[96])
+    assert np.array_equal(run["csv"][1:7].T, X[:, :6])
+
+
+def test_k2_optimum(run, orc):
+    """Newton-KKT from the all-zeros seed reproduces IPOPT's stored optimum at the learned theta."""
+    th = run["parameter_trace"][-1]
+    tg, X, U, Lam, info = orc.solve(run["ini_state"], 1.0, th, return_info=True)
+    assert info["status"] == "converged" and info["iters"] <= 10
+    assert np.abs(X - run["opt_state_traj"][::4]).max() < 1e-10
+    assert np.abs(U - run["opt_control_traj"][::4]).max() < 1e-10
+    assert abs(info["J"] - 11.7783742891) < 1e-9
+
+
+def test_k3_k4_loss_and_gradient(run, orc):
+    """loss_trace[0] and the gradient implied by the first Nesterov step, (theta0-theta1)/lr."""
+    th0 = run["parameter_trace"][0]
+    loss, dl, ex = orc.grad_iter(run["ini_state"], 1.0, th0, run["time_grid"], run["waypoints"])
+    assert abs(loss - run["loss_trace"][0]) / run["loss_trace"][0] < 1e-9
+    g = (run["parameter_trace"][0] - run["parameter_trace"][1]) / float(run["learning_rate"])
+    assert np.linalg.norm(dl - g) / np.linalg.norm(g) < 1e-6      # as-shipped BDF/RK45 path
+
+
+def test_k5_second_gradient(run, orc):
+    """Gradient at the first Nesterov look-ahead point: g_1 = (mu*v_1 - v_2)/lr."""
+    P = run["parameter_trace"]
+    mu, lr = float(run["mu"]), float(run["learning_rate"])
+    v1, v2 = P[1] - P[0], P[2] - P[1]
+    look = P[1] + mu * v1
+    g1 = (mu * v1 - v2) / lr
+    loss, dl, _ = orc.grad_iter(run["ini_state"], 1.0, look, run["time_grid"], run["waypoints"])
+    assert abs(loss - run["loss_trace"][1]) / run["loss_trace"][1] < 1e-9
+    assert np.linalg.norm(dl - g1) / np.linalg.norm(g1) < 1e-6
