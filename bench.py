@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--atol", type=float, default=1e-6)
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-deadline", type=float, default=200.0, help="stop starting new CPU-baseline steps after this many seconds")
     return ap.parse_args()
 
 
@@ -52,39 +53,67 @@ _ORC = None
 
 
 def _cpu_init(n_grid):
+    """Worker initialiser: one BLAS thread per worker (the oracle's linear algebra is 260x260 at most; the default
+    all-core BLAS pool in every worker oversubscribes a many-core host catastrophically)."""
     global _ORC
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:
+        pass
     from oracle import models
     from oracle.cpdp_oracle import Oracle
     _ORC = Oracle(models.quadrotor(), n_grid=n_grid)
 
 
+def _cpu_ready(_):
+    return os.getpid()
+
+
 def _cpu_one(job):
     x0, goal, theta, taus, wp = job
     _ORC.pd = goal
+    t0 = time.time()
     loss, dl, ex = _ORC.grad_iter(x0, 1.0, theta, taus, wp)       # as-shipped: BDF backward, RK45 forward
-    return loss, dl, ex["info"]["iters"]
+    return loss, dl, ex["info"]["iters"], time.time() - t0
 
 
-def cpu_baseline(n_grid, sample, steps=1, warmup=0):
-    """Oracle on `sample` problems of the same synthetic batch with one process per host core."""
+def cpu_baseline(n_grid, sample, steps=1, warmup=0, max_workers=0, deadline_s=240.0):
+    """Oracle (the CPU restatement of the reference algorithm) on a bounded sample of the same synthetic batch, one
+    process per host core.  Each step maps `sample` OCPs (default: one per worker) over the pool; the run stops
+    taking new steps after `deadline_s`.  Returns (cpu_baseline dict, seconds, steps done)."""
     from multiprocessing import Pool
     from lfsd_b200 import synthetic
     cores = os.cpu_count() or 1
-    sample = sample or cores
+    workers = min(cores, max_workers) if max_workers else cores
+    sample = sample or workers
+    workers = min(workers, sample)
     qb = synthetic.quad_batch(max(sample, 1))
     jobs = [(qb["x0"][b], qb["goal"][b], qb["theta"], qb["taus"], qb["wp"][b]) for b in range(sample)]
-    with Pool(min(cores, sample), initializer=_cpu_init, initargs=(n_grid,)) as pool:
+    t_pool = time.time()
+    with Pool(workers, initializer=_cpu_init, initargs=(n_grid,)) as pool:
+        pool.map(_cpu_ready, range(workers), chunksize=1)          # model build (sympy) is outside the timed region
+        print("[cpu_baseline] %d workers ready after %.1f s" % (workers, time.time() - t_pool), file=sys.stderr, flush=True)
         for _ in range(warmup):
-            pool.map(_cpu_one, jobs[:min(cores, sample)])
+            pool.map(_cpu_one, jobs[:workers], chunksize=1)
         t0 = time.time()
+        done = 0
+        per = []
         for _ in range(steps):
-            res = pool.map(_cpu_one, jobs)
+            res = pool.map(_cpu_one, jobs, chunksize=1)
+            per += [r[3] for r in res]
+            done += 1
+            print("[cpu_baseline] step %d: %.1f s elapsed, %.1f s per OCP per core" % (done, time.time() - t0, float(np.mean(per))),
+                  file=sys.stderr, flush=True)
+            if time.time() - t0 > deadline_s:
+                break
         dt = time.time() - t0
-    value = sample * steps / dt
-    return dict(value=value, unit=UNIT, cores=min(cores, sample), kind="port",
-                sample="%d OCPs (first indices of the seeded 4096-OCP batch), n_grid %d, %d step(s), %.1f s wall; "
-                       "oracle = numpy/scipy restatement (Newton-KKT + scipy BDF/RK45 as-shipped), one process per core"
-                       % (sample, n_grid, steps, dt)), dt, steps
+    value = sample * done / dt
+    return dict(value=value, unit=UNIT, cores=workers, kind="port",
+                sample="%d OCPs per step (first indices of the seeded 4096-OCP batch), n_grid %d, %d step(s), %.1f s wall, "
+                       "%.1f s per OCP per core; oracle = numpy/scipy restatement of the reference algorithm (Newton-KKT in "
+                       "place of IPOPT, scipy BDF/RK45 as shipped), one single-threaded process per host core (%d cores)"
+                       % (sample, n_grid, done, dt, float(np.mean(per)), cores)), dt, done
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -134,9 +163,12 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def flop_model(info, n, m, r, N, S, iters_sum, B, counters_sum, mode):
-    """Executed useful fp64 flops of one step: op counts of the generated model code after CSE plus
-    the dense/sparse linear algebra around it, times the Newton-iteration / rhs-evaluation counters the kernels record."""
+def flop_model(info, n, m, r, N, S, iters_sum, B, cnt, mode):
+    """Executed useful fp64 flops of one step: op counts of the generated model code after CSE
+    plus the sparse / packed-symmetric linear algebra around it, times the counters the kernels record (Newton
+    iterations, rhs evaluations, LU factorisations).  cnt = summed counters [back rhs, back steps, fwd rhs, fwd steps,
+    back LU, back Jacobians].  These are the flops of OUR formulation (sparsity and symmetry exploited), i.e. a lower
+    bound on the dense algorithmic counts of SURVEY.md 8d."""
     nz = n + m
     stages = 4 * S
     per_int = stages * (2 * info["ops_fc"] + info["ops_hgrad"] + 8 * n)                     # k_stage_adjoint
@@ -144,13 +176,22 @@ def flop_model(info, n, m, r, N, S, iters_sum, B, counters_sum, mode):
     per_int += 2 * n * n * nz + 2 * nz * nz * n + 2 * m * m * (n + 1) + 2 * n * n * m + 4 * n * nz + stages * info["ops_fc"]
     solve = iters_sum * N * per_int
     nnzx, nnzu = info["nnz_fx"], info["nnz_fu"]
-    ric = info["ops_pmp"] + 2 * nnzu * (n + r) + 2 * m * m * n + (n * (n + 1) // 2) * (4 * nnzx / n * 1.0 + 4 * m) \
-        + n * r * (2 * nnzx / n + 2 + 2 * m)
-    fwd = info["ops_pmp"] + 2 * nnzu * (n + r) + 2 * m * m * (n + r) + 2 * m * n * r + n * r * (2 * nnzx / n + 2 * nnzu / n + 1) \
-        + 4 * (n * (n + 1) // 2 + n * r)
-    ny_r, ny_f = n * (n + 1) // 2 + n * r, n * r
-    aux = counters_sum[0] * (ric + 16 * ny_r) + counters_sum[2] * (fwd + 16 * ny_f)
-    return dict(solve=float(solve), aux=float(aux), total=float(solve + aux))
+    nt = n * (n + 1) // 2
+    ric = 2 * nnzu * (n + r) + 2 * m * m * n + nt * (4 * nnzx / n * 1.0 + 4 * m) + n * r * (2 * nnzx / n + 2 + 2 * m)
+    pmp = info["ops_pmp"] + 2 * (2 * n + m) * 3 + 2 * m ** 3
+    fwd = pmp + 2 * nnzu * (n + r) + 2 * m * m * (n + r) + 2 * m * n * r + n * r * (2 * nnzx / n + 2 * nnzu / n + 1) \
+        + 4 * (nt + n * r)
+    ny_r, ny_f = nt + n * r, n * r
+    if mode == "bdf":
+        # per rhs evaluation: Riccati rhs + Newton residual/solve (packed LU triangular solves + W block) + norms;
+        # per step: PMP matrices at t_new, predictor/psi/difference update; per LU: packed (nt) and n x n factorisations
+        back = cnt[0] * (ric + 2 * nt * nt + 2 * n * n * r + 2 * n * n * r + 8 * ny_r) \
+            + cnt[1] * (pmp + 30 * ny_r) + cnt[4] * (2.0 / 3 * nt ** 3 + 2.0 / 3 * n ** 3 + 4 * n * nt) \
+            + cnt[5] * (2 * n * n * m * 2 + 2 * n ** 3 + 2 * n * n * r)
+    else:
+        back = cnt[0] * (ric + pmp * 6.0 / 7 + 16 * ny_r)
+    fwdf = cnt[2] * (fwd + 16 * ny_f)
+    return dict(solve=float(solve), aux_backward=float(back), aux_forward=float(fwdf), total=float(solve + back + fwdf))
 
 
 def run_ours(a):
@@ -219,11 +260,13 @@ def run_ours(a):
     sync_all()
     ev[0].record()
     for _ in range(a.steps):
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         e0.record()
         sol = oc.cocSolverBatch(resident["x0"], 1.0, resident["theta"], pdata=resident["goal"])
         e1.record()
-        aux = oc.auxSysSolverBatch(sol, resident["taus"], resident["wp"], qb["sel"])
+        aux = oc.auxSysSolverBatch(sol, resident["taus"], resident["wp"], qb["sel"], phases=1)     # backward kernel alone
+        e2.record()
+        aux = oc.auxSysSolverBatch(sol, resident["taus"], resident["wp"], qb["sel"], phases=2, out=aux)
         rows = torch.cat([aux["loss"].unsqueeze(1), aux["dtheta"]], dim=1)
         if world > 1:
             dist.all_gather_into_tensor(gathered, rows)
@@ -231,8 +274,8 @@ def run_ours(a):
         else:
             allrows = rows
         red = oc.reduceBatch(allrows[:, 0].contiguous(), allrows[:, 1:].contiguous())
-        e2.record()
-        ph.append((e0, e1, e2))
+        e3.record()
+        ph.append((e0, e1, e2, e3))
     ev[1].record()
     sync_all()
     ms = ev[0].elapsed_time(ev[1])
@@ -242,7 +285,8 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     solve_ms = float(np.mean([p[0].elapsed_time(p[1]) for p in ph]))
-    aux_ms = float(np.mean([p[1].elapsed_time(p[2]) for p in ph]))
+    back_ms = float(np.mean([p[1].elapsed_time(p[2]) for p in ph]))
+    fwd_ms = float(np.mean([p[2].elapsed_time(p[3]) for p in ph]))
     rounds = lib.last_rounds()
 
     # ---- timed region 2: end to end through the public API with HOST buffers ---------------------------------
@@ -261,6 +305,19 @@ def run_ours(a):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     ms_e2e = float(t2.item())
 
+    # ---- FP64 pipe peak, measured on this GPU (MEASURED_PEAKS.json has no fp64 entry) --------------------------
+    peak_tf = None
+    if rank == 0:
+        best = 1e30
+        for _ in range(4):
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            fl = oc.fp64PeakProbe(148 * 8, 100000)
+            p1.record()
+            torch.cuda.synchronize()
+            best = min(best, p0.elapsed_time(p1))
+        peak_tf = fl / (best / 1e3) / 1e12
+
     # ---- statistics -----------------------------------------------------------------------------------------
     status = sol["status"].cpu().numpy()
     iters = sol["iters"].cpu().numpy()
@@ -275,36 +332,54 @@ def run_ours(a):
             dist.destroy_process_group()
         return
     info = oc.codegen_info
-    fm = flop_model(info, oc.n_state, oc.n_control, r, a.n_grid, oc.steps_per_grid, loc[0], B_total, loc[3:7], mode)
+    fm = flop_model(info, oc.n_state, oc.n_control, r, a.n_grid, oc.steps_per_grid, loc[0], B_total, loc[3:9], mode)
     step_s = ms / a.steps / 1e3
     value = B_total * a.steps / (ms / 1e3)
-    peak_tf = 148 * 64 * 2 * 1.965e9 / 1e12        # nominal B200 DFMA peak (no fp64 entry in MEASURED_PEAKS.json)
-    achieved_tf = fm["total"] / world / step_s / 1e12
+    nominal_tf = 148 * 64 * 2 * 1.965e9 / 1e12
+    # roofline of the dominant kernel: the backward Riccati sweep (one launch per step, timed alone with CUDA events)
+    kname = "k_riccati_bdf" if mode == "bdf" else "k_riccati_rk45"
+    dom_flops = fm["aux_backward"] / world
+    achieved_tf = dom_flops / (back_ms / 1e3) / 1e12
+    mp = {}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%d quadrotor OCPs%s (n=13,m=4,r=7), n_grid %d, S=4, T=1, shared theta0, "
-                               "rng default_rng(20210308); SURVEY.md 8d" % (a.batch, " per GPU" if a.scaling == "weak" else " total", a.n_grid),
-                   "global_batch": B_total, "aux_mode": mode, "rtol_back": a.rtol, "atol_back": a.atol,
+        "config": {"workload": "%d quadrotor OCPs%s (n=13,m=4,r=7), n_grid 50, S=4, T=1, shared theta0, "
+                               "rng default_rng(20210308); SURVEY.md 8d / BASELINE.json configs[4]" % (a.batch, " per GPU" if a.scaling == "weak" else " total"),
+                   "n_grid": a.n_grid, "global_batch": B_total, "aux_mode": mode, "rtol_back": a.rtol, "atol_back": a.atol,
                    "parallelism": "dp%d contiguous shards, all-gather of per-OCP (loss,dtheta) rows + fixed-tree sum" % world,
-                   "l2": "per-step working set (~%.1f GB workspace) exceeds the 126 MB L2" % (lib.workspace_bytes(Bl, a.n_grid, 4) / 1e9)},
+                   "l2": "inputs larger than L2: per-step working set (~%.1f GB workspace + outputs) exceeds the 126 MB L2, "
+                         "every step starts from the zero seed" % (lib.workspace_bytes(Bl, a.n_grid, 4) / 1e9)},
         "e2e": {"value": B_total * a.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": (r + 1) * 8},
         "gpu_launches": a.steps * (2 + 4 * rounds + 2 + 1),
         "clocks": clocks,
-        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": None,
-                     "note": "whole-step executed fp64 flops (DESIGN.md flop model x recorded Newton-iteration / rhs counters) "
-                             "per GPU / step time; peak = nominal 148 SM x 64 DFMA x 2 x 1.965 GHz (MEASURED_PEAKS.json has no fp64 figure)",
-                     "flops_per_step": fm, "phase_ms": {"solve": solve_ms, "aux_loss_reduce": aux_ms}},
+        "roofline": {"bound": "fp64", "kernel": kname, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                     "kernel_ms": back_ms,
+                     "note": "dominant kernel = backward Riccati sweep, one launch per step, timed alone with CUDA events; "
+                             "achieved = executed useful fp64 flops of that launch (DESIGN.md flop model x the rhs / step / LU "
+                             "counters the kernel records) / its duration; peak = DFMA throughput measured in this run with "
+                             "cpdp_dfma_probe (nominal 148 SM x 64 lanes x 2 x 1.965 GHz = %.1f TFLOP/s); the path is "
+                             "fp64-compute/latency bound, not HBM bound: see hbm_gbs" % nominal_tf,
+                     "whole_step": {"achieved": fm["total"] / world / step_s / 1e12,
+                                    "frac": (fm["total"] / world / step_s / 1e12 / peak_tf) if peak_tf else None},
+                     "hbm_gbs": {"achieved": None, "peak": mp.get("hbm_gbs")},
+                     "flops_per_step": fm,
+                     "phase_ms": {"solve": solve_ms, "aux_backward": back_ms, "aux_forward_loss_reduce": fwd_ms}},
         "stats": {"newton_iters_mean": loc[0] / B_total, "newton_rounds": rounds, "not_converged": int(loc[1]),
                   "aux_failed": int(loc[2]), "back_rhs_mean": loc[3] / B_total, "back_steps_mean": loc[4] / B_total,
                   "fwd_rhs_mean": loc[5] / B_total, "fwd_steps_mean": loc[6] / B_total,
+                  "back_lu_mean": loc[7] / B_total, "back_jac_mean": loc[8] / B_total,
                   "loss_sum": float(red[0].item())},
     }
     if world == 1 and not a.no_cpu_baseline:
-        cb, _, _ = cpu_baseline(a.n_grid, a.cpu_sample)
+        cb, _, _ = cpu_baseline(a.n_grid, a.cpu_sample, deadline_s=a.cpu_deadline)
         out["cpu_baseline"] = cb
     print(json.dumps(out))
     if world > 1:
@@ -316,8 +391,8 @@ def run_reference(a):
     if rank != 0:
         return
     import lfsd_b200  # noqa: F401
-    cb, dt, steps = cpu_baseline(a.n_grid, a.cpu_sample, steps=a.steps, warmup=min(a.warmup, 1))
-    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+    cb, dt, steps = cpu_baseline(a.n_grid, a.cpu_sample, steps=a.steps, warmup=0, deadline_s=a.cpu_deadline)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
            "warmup": a.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": a.scaling,
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": "%d quadrotor OCPs per step (bounded sample of the 4096-OCP batch), n_grid %d" % (cb["cores"], a.n_grid),

@@ -28,6 +28,10 @@ int cpdp_model_dims(int* n, int* m, int* r, int* q);
 /* Length of one packed Riccati node [upper-tri(P) | W] = n(n+1)/2 + n*r (internal table of auxSysSolver). */
 int cpdp_riccati_state_dim(void);
 
+/* 1 if mode 1 (as-shipped BDF backward sweep) of cpdp_aux is compiled in; ints per row of `counters`. */
+int cpdp_has_bdf(void);
+int cpdp_num_counters(void);
+
 /* Bytes of scratch the caller must provide to cpdp_solve / cpdp_aux for (B, N, S). */
 size_t cpdp_workspace_bytes(int B, int N, int S);
 
@@ -56,14 +60,29 @@ int cpdp_last_rounds(void);
  *   Loss: W waypoints of D observed state components sel[D] (host ints); taus[B][W] (taus_stride = W) or shared
  *   taus[W] (stride 0); wp[B][W][D].  W = 0 skips the loss.
  * Outputs Xa[B][N+1][n*r] (dx/dtheta nodes), Ua[B][N+1][m*r], loss[B], dtheta[B][r] (reference convention:
- * dl_dy = y - wp, i.e. half the true gradient), aux_status[B] (0 ok), counters[B][4]
- * (backward rhs evals, backward steps, forward rhs evals, forward steps). */
+ * dl_dy = y - wp, i.e. half the true gradient), aux_status[B] (0 ok, 1 step too small, 2 non-finite, 3 skipped
+ * because the forward solve produced no trajectory, 4 singular Newton matrix), counters[B][cpdp_num_counters()=6]
+ * (backward rhs evals, backward steps, forward rhs evals, forward steps, backward LU factorisations, backward
+ * Jacobian evaluations). */
 int cpdp_aux(void* ws, size_t ws_bytes, int B, int N, int S, double T,
              const double* theta, int theta_stride, const double* pdata,
              const double* X, const double* U, const double* Lam, const int* solve_status,
              int mode, double rtol_b, double atol_b, double rtol_f, double atol_f,
              int W, int D, const int* sel /* host */, const double* taus, int taus_stride, const double* wp,
              double* Xa, double* Ua, double* loss, double* dtheta, int* aux_status, int* counters, void* stream);
+
+/* cpdp_aux with the two sweeps selectable: phases 1 = backward Riccati sweep only (node table left in ws),
+ * 2 = forward sweep + loss only (needs the table of a previous phase-1 call on the same ws), 3 = both. */
+int cpdp_aux_phases(void* ws, size_t ws_bytes, int B, int N, int S, double T,
+             const double* theta, int theta_stride, const double* pdata,
+             const double* X, const double* U, const double* Lam, const int* solve_status,
+             int mode, double rtol_b, double atol_b, double rtol_f, double atol_f,
+             int W, int D, const int* sel /* host */, const double* taus, int taus_stride, const double* wp,
+             double* Xa, double* Ua, double* loss, double* dtheta, int* aux_status, int* counters, void* stream, int phases);
+
+/* FP64 FMA throughput probe used by bench.py for the roofline denominator: one kernel of `blocks` x 256 threads,
+ * 8 independent chains of `iters` DFMAs per thread (flops = blocks*256*8*iters*2).  sink: >= 1 device double. */
+int cpdp_dfma_probe(double* sink, int blocks, int iters, void* stream);
 
 /* Cross-problem sum of [loss | dL/dtheta] rows in a fixed binary tree over the row index (bit-identical for any
  * sharding of the rows over GPUs once they are all-gathered).  scratch: nextpow2(B)*(1+r) doubles; out[1+r]. */

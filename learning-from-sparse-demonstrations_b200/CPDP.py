@@ -270,10 +270,12 @@ class COCSys:
                    theta=th, theta_stride=th_stride, pdata=pd, B=B, x0=x0)
         return out
 
-    def auxSysSolverBatch(self, sol, taus=None, waypoints=None, sel=None, mode=None):
+    def auxSysSolverBatch(self, sol, taus=None, waypoints=None, sel=None, mode=None, phases=3, out=None):
         """Batched auxSysSolver (+ fused loss closure).  ``sol`` is the dict returned by cocSolverBatch.
         taus [W] or [B,W]; waypoints [B,W,D] (or [W,D] shared by B=1); sel = observed state indices.
-        Returns dict with Xa [B,N+1,n*r], Ua [B,N+1,m*r], loss [B], dtheta [B,r], aux_status, counters."""
+        Returns dict with Xa [B,N+1,n*r], Ua [B,N+1,m*r], loss [B], dtheta [B,r], aux_status, counters.
+        phases: 1 = backward Riccati sweep only, 2 = forward sweep + loss only (pass the dict of the phase-1 call
+        as ``out``), 3 = both (default)."""
         lib = self.build()
         mem = self._device()
         B, N, S = sol["B"], self.n_grid, self.steps_per_grid
@@ -295,15 +297,26 @@ class COCSys:
             wp_h = waypoints if hasattr(waypoints, 'data_ptr') else numpy.asarray(waypoints, dtype=float).reshape(B, W, D)
             wp_d = mem.from_host(wp_h)
         ws = self._workspace(B)
-        out = dict(Xa=mem.empty((B, N + 1, n * r)), Ua=mem.empty((B, N + 1, m * r)), loss=mem.empty((B,)),
-                   dtheta=mem.empty((B, r)), aux_status=mem.zeros((B,), "i4"), counters=mem.zeros((B, 4), "i4"))
+        if out is None:
+            out = dict(Xa=mem.empty((B, N + 1, n * r)), Ua=mem.empty((B, N + 1, m * r)), loss=mem.empty((B,)),
+                       dtheta=mem.empty((B, r)), aux_status=mem.zeros((B,), "i4"),
+                       counters=mem.zeros((B, lib.ncounters), "i4"))
         lib.aux(mem.ptr(ws), self._ws_bytes, B, N, S, sol["horizon"], mem.ptr(sol["theta"]), sol["theta_stride"],
                 mem.ptr(sol["pdata"]), mem.ptr(sol["X"]), mem.ptr(sol["U"]), mem.ptr(sol["Lam"]), mem.ptr(sol["status"]),
                 int(mode), float(self.rtol_back), float(self.atol_back), float(self.rtol_fwd), float(self.atol_fwd),
                 W, D, sel, mem.ptr(tau_d), tau_stride, mem.ptr(wp_d),
                 mem.ptr(out["Xa"]), mem.ptr(out["Ua"]), mem.ptr(out["loss"]), mem.ptr(out["dtheta"]),
-                mem.ptr(out["aux_status"]), mem.ptr(out["counters"]), mem.stream())
+                mem.ptr(out["aux_status"]), mem.ptr(out["counters"]), mem.stream(), phases=phases)
         return out
+
+    def fp64PeakProbe(self, blocks, iters):
+        """Launches the library's DFMA throughput probe (bench.py roofline denominator); returns its flop count."""
+        lib = self.build()
+        mem = self._device()
+        if not hasattr(self, '_sink'):
+            self._sink = mem.zeros((8,))
+        lib.dfma_probe(mem.ptr(self._sink), int(blocks), int(iters), mem.stream())
+        return float(blocks) * 256 * 8 * iters * 2
 
     def reduceBatch(self, loss, dtheta):
         """Fixed-tree sum over problems: returns device array [1+r] = [sum loss | sum dL/dtheta]."""

@@ -93,6 +93,10 @@ class CpdpLib:
                                _i, _d, _d, _d, _d, _i, _i, ctypes.POINTER(_i), _vp, _i, _vp,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp]
         L.cpdp_aux.restype = _i
+        L.cpdp_aux_phases.argtypes = L.cpdp_aux.argtypes + [_i]
+        L.cpdp_aux_phases.restype = _i
+        L.cpdp_dfma_probe.argtypes = [_vp, _i, _i, _vp]
+        L.cpdp_dfma_probe.restype = _i
         L.cpdp_reduce.argtypes = [_vp, _vp, _i, _vp, _vp, _vp]
         L.cpdp_reduce.restype = _i
         if hasattr(L, "cpdp_error_string"):
@@ -102,6 +106,10 @@ class CpdpLib:
         L.cpdp_model_dims(ctypes.byref(n), ctypes.byref(m), ctypes.byref(r), ctypes.byref(q))
         self.n, self.m, self.r, self.q = n.value, m.value, r.value, q.value
         self.nyr = L.cpdp_riccati_state_dim()
+        L.cpdp_num_counters.restype = _i
+        L.cpdp_has_bdf.restype = _i
+        self.ncounters = int(L.cpdp_num_counters())
+        self.has_bdf = bool(L.cpdp_has_bdf())
 
     def check(self, rc, what):
         if rc != 0:
@@ -121,11 +129,18 @@ class CpdpLib:
 
     def aux(self, ws, ws_bytes, B, N, S, T, theta, theta_stride, pdata, X, U, Lam, solve_status,
             mode, rtol_b, atol_b, rtol_f, atol_f, W, D, sel, taus, taus_stride, wp,
-            Xa, Ua, loss, dtheta, aux_status, counters, stream):
+            Xa, Ua, loss, dtheta, aux_status, counters, stream, phases=3):
         sel_arr = (_i * max(1, len(sel)))(*sel) if sel else (_i * 1)(0)
-        self.check(self.L.cpdp_aux(ws, ws_bytes, B, N, S, T, theta, theta_stride, pdata, X, U, Lam, solve_status,
-                                   mode, rtol_b, atol_b, rtol_f, atol_f, W, D, sel_arr, taus, taus_stride, wp,
-                                   Xa, Ua, loss, dtheta, aux_status, counters, stream), "cpdp_aux")
+        args = (ws, ws_bytes, B, N, S, T, theta, theta_stride, pdata, X, U, Lam, solve_status,
+                mode, rtol_b, atol_b, rtol_f, atol_f, W, D, sel_arr, taus, taus_stride, wp,
+                Xa, Ua, loss, dtheta, aux_status, counters, stream)
+        if phases == 3:
+            self.check(self.L.cpdp_aux(*args), "cpdp_aux")
+        else:
+            self.check(self.L.cpdp_aux_phases(*(args + (phases,))), "cpdp_aux_phases")
+
+    def dfma_probe(self, sink, blocks, iters, stream):
+        self.check(self.L.cpdp_dfma_probe(sink, blocks, iters, stream), "cpdp_dfma_probe")
 
     def reduce(self, loss, dtheta, B, scratch, out, stream):
         self.check(self.L.cpdp_reduce(loss, dtheta, B, scratch, out, stream), "cpdp_reduce")

@@ -73,6 +73,11 @@ CPDP_API int cpdp_model_dims(int* n, int* m, int* r, int* q) {
 
 CPDP_API int cpdp_riccati_state_dim(void) { return CPDP_NS::NYR; }
 
+// Present when the library contains the as-shipped BDF backward sweep (mode 1 of cpdp_aux).
+CPDP_API int cpdp_has_bdf(void) { return 1; }
+
+CPDP_API int cpdp_num_counters(void) { return CPDP_NS::NCOUNTERS; }
+
 CPDP_API size_t cpdp_workspace_bytes(int B, int N, int S) {
     if (B <= 0 || N <= 0 || S <= 0) return 0;
     return CPDP_NS::ws_carve(nullptr, B, N, S).bytes;
@@ -118,18 +123,20 @@ CPDP_API int cpdp_solve(void* ws, size_t ws_bytes, int B, int N, int S, double T
 }
 
 // Auxiliary system + loss (COCSys.auxSysSolver, CPDP.py:301-381; loss closures QuadAlgorithm.py:616-639).
-// mode 0: backward Riccati sweep with RK45 (rtol_b, atol_b); mode 1: BDF emulation of the as-shipped reference.
-CPDP_API int cpdp_aux(void* ws, size_t ws_bytes, int B, int N, int S, double T,
+// mode 0: backward Riccati sweep with RK45 (rtol_b, atol_b); mode 1: BDF scheme of the as-shipped reference.
+// phases: bit 0 = backward Riccati sweep (node table into the workspace), bit 1 = forward sweep + loss.
+static int cpdp_aux_impl(void* ws, size_t ws_bytes, int B, int N, int S, double T,
              const double* theta, int theta_stride, const double* pdata,
              const double* X, const double* U, const double* Lam, const int* solve_status,
              int mode, double rtol_b, double atol_b, double rtol_f, double atol_f,
              int W, int D, const int* sel_host, const double* taus, int taus_stride, const double* wp,
-             double* Xa, double* Ua, double* loss, double* dtheta, int* aux_status, int* counters, void* stream) {
+             double* Xa, double* Ua, double* loss, double* dtheta, int* aux_status, int* counters, void* stream, int phases) {
     using namespace CPDP_NS;
     if (!ws || B <= 0 || N <= 0 || !theta || !X || !U || !Lam || !Xa || !Ua || !loss || !dtheta || !aux_status || !counters) return -1;
     if (theta_stride != 0 && theta_stride != NP) return -2;
     if (W < 0 || D < 0 || D > MAX_SEL || (W > 0 && (!taus || !wp || !sel_host))) return -4;
     if (W > 0 && taus_stride != 0 && taus_stride != W) return -5;
+    if (mode != 0 && mode != 1) return -7;
     WsLayout w = ws_carve((char*)ws, B, N, S);
     if (w.bytes > ws_bytes) return -3;
     AuxArgs a;
@@ -145,14 +152,52 @@ CPDP_API int cpdp_aux(void* ws, size_t ws_bytes, int B, int N, int S, double T,
     a.loss = loss; a.dtheta = dtheta; a.solve_status = solve_status; a.aux_status = aux_status; a.counters = counters;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t ric_bytes = RIC_SMEM_DOUBLES * sizeof(double), fwd_bytes = FWD_SMEM_DOUBLES * sizeof(double);
-    if (mode == 0) {
-        CPDP_PREPARE_SMEM(k_riccati_rk45, ric_bytes);
-        CPDP_LAUNCH(k_riccati_rk45, B, AUX_THREADS, ric_bytes, st, a);
-    } else {
-        return -7;
+    if (phases & 1) {
+        if (mode == 0) {
+            CPDP_PREPARE_SMEM(k_riccati_rk45, ric_bytes);
+            CPDP_LAUNCH(k_riccati_rk45, B, AUX_THREADS, ric_bytes, st, a);
+        } else {
+            const size_t bdf_bytes = BDF_SMEM_DOUBLES * sizeof(double);
+            CPDP_PREPARE_SMEM(k_riccati_bdf, bdf_bytes);
+            CPDP_LAUNCH(k_riccati_bdf, B, BDF_THREADS, bdf_bytes, st, a);
+        }
     }
-    CPDP_PREPARE_SMEM(k_aux_forward, fwd_bytes);
-    CPDP_LAUNCH(k_aux_forward, B, AUX_THREADS, fwd_bytes, st, a);
+    if (phases & 2) {
+        CPDP_PREPARE_SMEM(k_aux_forward, fwd_bytes);
+        CPDP_LAUNCH(k_aux_forward, B, AUX_THREADS, fwd_bytes, st, a);
+    }
+    return CPDP_LAST_ERROR();
+}
+
+CPDP_API int cpdp_aux(void* ws, size_t ws_bytes, int B, int N, int S, double T,
+             const double* theta, int theta_stride, const double* pdata,
+             const double* X, const double* U, const double* Lam, const int* solve_status,
+             int mode, double rtol_b, double atol_b, double rtol_f, double atol_f,
+             int W, int D, const int* sel_host, const double* taus, int taus_stride, const double* wp,
+             double* Xa, double* Ua, double* loss, double* dtheta, int* aux_status, int* counters, void* stream) {
+    return cpdp_aux_impl(ws, ws_bytes, B, N, S, T, theta, theta_stride, pdata, X, U, Lam, solve_status, mode, rtol_b, atol_b,
+                         rtol_f, atol_f, W, D, sel_host, taus, taus_stride, wp, Xa, Ua, loss, dtheta, aux_status, counters, stream, 3);
+}
+
+// Same arguments as cpdp_aux plus `phases` (1 = backward sweep only, 2 = forward sweep + loss only, 3 = both), so
+// that a caller can time or overlap the two sweeps separately.  Phase 2 needs the node table phase 1 left in `ws`.
+CPDP_API int cpdp_aux_phases(void* ws, size_t ws_bytes, int B, int N, int S, double T,
+             const double* theta, int theta_stride, const double* pdata,
+             const double* X, const double* U, const double* Lam, const int* solve_status,
+             int mode, double rtol_b, double atol_b, double rtol_f, double atol_f,
+             int W, int D, const int* sel_host, const double* taus, int taus_stride, const double* wp,
+             double* Xa, double* Ua, double* loss, double* dtheta, int* aux_status, int* counters, void* stream, int phases) {
+    if (phases < 1 || phases > 3) return -9;
+    return cpdp_aux_impl(ws, ws_bytes, B, N, S, T, theta, theta_stride, pdata, X, U, Lam, solve_status, mode, rtol_b, atol_b,
+                         rtol_f, atol_f, W, D, sel_host, taus, taus_stride, wp, Xa, Ua, loss, dtheta, aux_status, counters, stream, phases);
+}
+
+// FP64 FMA throughput probe (roofline denominator of bench.py: MEASURED_PEAKS.json carries no fp64 figure).
+// Launches one kernel of blocks x 256 threads, each thread running 8 independent chains of `iters` DFMAs;
+// flops = blocks * 256 * 8 * iters * 2.  sink: >= 1 double of device memory.
+CPDP_API int cpdp_dfma_probe(double* sink, int blocks, int iters, void* stream) {
+    if (!sink || blocks <= 0 || iters <= 0) return -1;
+    CPDP_LAUNCH(k_dfma_probe, blocks, 256, 0, (cudaStream_t)stream, sink, iters);
     return CPDP_LAST_ERROR();
 }
 

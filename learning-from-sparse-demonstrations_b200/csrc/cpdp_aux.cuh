@@ -22,6 +22,7 @@ constexpr int MSZ = Model::PMP_SIZE + NU * NU; // dense PMP matrices + inverse o
 constexpr int NSLOT = 5;                       // distinct stage times of one Dormand-Prince step
 constexpr int AUX_THREADS = 64;
 constexpr int MAX_SEL = 16;
+constexpr int NCOUNTERS = 6;                    // per-problem counters: back rhs, back steps, fwd rhs, fwd steps, back LU, back Jacobians
 
 struct AuxArgs {
     int B, N;
@@ -41,7 +42,7 @@ struct AuxArgs {
     double* dtheta;        // [B][NP]
     const int* solve_status;   // [B] (problems that did not converge are skipped; may be null)
     int* aux_status;       // [B]  0 ok, 1 step too small, 2 non-finite
-    int* counters;         // [B][4]  backward rhs, backward steps, forward rhs, forward steps
+    int* counters;         // [B][NCOUNTERS]
 };
 
 CPDP_HD int tri(int i, int j) { return i * NX - (i * (i - 1)) / 2 + (j - i); }   // i <= j
@@ -506,7 +507,7 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
         for (int q = tid; q < NYR; q += nt) PW[(size_t)(k - 1) * NYR + q] = y[q];
         __syncthreads();
     }
-    if (tid == 0) { a.aux_status[b] = st; a.counters[b * 4 + 0] = nrhs; a.counters[b * 4 + 1] = nsteps; }
+    if (tid == 0) { a.aux_status[b] = st; a.counters[b * NCOUNTERS + 0] = nrhs; a.counters[b * NCOUNTERS + 1] = nsteps; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -554,7 +555,7 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_aux_forward(AuxArgs a) {
         for (int q = tid; q < NYF; q += nt) Xa[(size_t)(k + 1) * NYF + q] = y[q];
         __syncthreads();
     }
-    if (tid == 0) { a.aux_status[b] = st; a.counters[b * 4 + 2] = nrhs; a.counters[b * 4 + 3] = nsteps; }
+    if (tid == 0) { a.aux_status[b] = st; a.counters[b * NCOUNTERS + 2] = nrhs; a.counters[b * NCOUNTERS + 3] = nsteps; }
     // ---- loss and gradient (thread i < NP accumulates dL[i]; thread 0 the loss)
     const double* taus = a.taus + (size_t)b * a.taus_stride;
     const double* wp = a.wp + (size_t)b * a.W * a.D;

@@ -274,18 +274,38 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS) k_stage_hessian(SolveArgs a) {
 // ------------------------------------------------------------------------------------------------
 // small dense helpers used by one CTA (all threads call; results valid after the trailing barrier)
 // ------------------------------------------------------------------------------------------------
+// Block-wide sum / max returned to every thread.  Order of operations (identical on the GPU and in the host
+// emulation, so both produce the same bits): xor-butterfly inside each group of 32 threads, then the group results
+// are combined sequentially in group order by every thread.  blockDim.x must be a multiple of 32; `red` needs
+// blockDim.x doubles (emulation) / blockDim.x/32 doubles (GPU).  All threads of the CTA must call it.
 CPDP_D double block_reduce(double v, double* red, bool is_max) {
     const int tid = threadIdx.x, nt = blockDim.x;
+#ifdef __CUDACC__
+    for (int o = 16; o > 0; o >>= 1) {
+        const double x = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmax(v, x) : (v + x);
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double r = red[0];
+    for (int i = 1; i < (nt >> 5); ++i) r = is_max ? fmax(r, red[i]) : (r + red[i]);
+    return r;
+#else
+    for (int o = 16; o > 0; o >>= 1) {
+        __syncthreads();
+        red[tid] = v;
+        __syncthreads();
+        const double x = red[tid ^ o];
+        v = is_max ? fmax(v, x) : (v + x);
+    }
     __syncthreads();
     red[tid] = v;
     __syncthreads();
-    if (tid == 0) {
-        double r = red[0];
-        for (int i = 1; i < nt; ++i) r = is_max ? fmax(r, red[i]) : (r + red[i]);
-        red[nt] = r;
-    }
-    __syncthreads();
-    return red[nt];
+    double r = red[0];
+    for (int i = 32; i < nt; i += 32) r = is_max ? fmax(r, red[i]) : (r + red[i]);
+    return r;
+#endif
 }
 
 // In-place Cholesky of an n x n SPD matrix (row-major, lower triangle used). Returns false if not PD.
@@ -602,6 +622,19 @@ CPDP_GLOBAL void k_solve_init(SolveArgs a) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)a.B; i += gs) {
         a.status[i] = ST_RUNNING; a.iters[i] = 0; a.nu[i] = 0.0; a.dlast[i] = 0.0; a.J[i] = 0.0; a.kkt[i] = 0.0;
     }
+}
+
+// k_dfma_probe: 8 independent DFMA chains per thread (FP64 pipe throughput probe for the bench roofline).
+CPDP_GLOBAL void __launch_bounds__(256) k_dfma_probe(double* sink, int iters) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3, a4 = a0 + 4e-3, a5 = a0 + 5e-3,
+           a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double m = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+        a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) sink[0] = r;          // never true: keeps the chains alive
 }
 
 // k_compact: ordered list of the problems that are still iterating (single CTA).

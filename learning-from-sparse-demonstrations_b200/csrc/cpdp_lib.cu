@@ -8,9 +8,7 @@
 #include CPDP_MODEL_HEADER
 #include "cpdp_kernels.cuh"
 #include "cpdp_aux.cuh"
-#ifdef CPDP_WITH_BDF
 #include "cpdp_bdf.cuh"
-#endif
 
 static int g_last_error = 0;
 static int g_sms = 0;
@@ -67,6 +65,7 @@ extern "C" CPDP_API const char* cpdp_error_string(int code) {
             case -6: return "observed state index out of range";
             case -7: return "unknown integrator mode";
             case -8: return "model has per-problem constants but pdata is null";
+            case -9: return "phases must be 1, 2 or 3";
             default: return "invalid argument";
         }
     }

@@ -85,6 +85,10 @@ class _Fns:
         self.term = lam([x, th, pd], [h, hx, hx.jacobian(x), hx.jacobian(th)])
 
 
+class OracleIntegrationError(RuntimeError):
+    pass
+
+
 class Oracle:
     def __init__(self, model, n_grid=10, steps_per_grid=4):
         self.model = model
@@ -349,6 +353,8 @@ class Oracle:
         for k in range(N, 0, -1):
             t_span = [time_grid[k], time_grid[k - 1]]
             sol = solve_ivp(vec_PW_ode, t_span, PW[k, :], t_eval=[t_span[1]], **back)
+            if sol.status != 0:       # the reference would crash on the empty sol.y here (CPDP.py:336)
+                raise OracleIntegrationError('backward sweep failed on interval %d: %s' % (k, sol.message))
             PW[k - 1, :] = sol.y.flatten()
         PW_sol = interp1d(time_grid, PW, axis=0)
 
@@ -371,6 +377,8 @@ class Oracle:
         for k in range(N):
             t_span = [time_grid[k], time_grid[k + 1]]
             sol = solve_ivp(vec_aux_ode, t_span, Xa[k, :], t_eval=[time_grid[k + 1]], **fwd)
+            if sol.status != 0:
+                raise OracleIntegrationError('forward sweep failed on interval %d: %s' % (k, sol.message))
             Xa[k + 1, :] = sol.y.flatten()
             x, u, lam = split(float(time_grid[k + 1]))
             P, W = PWat(float(time_grid[k + 1]))

@@ -11,9 +11,7 @@
 #include CPDP_MODEL_HEADER
 #include "cpdp_kernels.cuh"
 #include "cpdp_aux.cuh"
-#ifdef CPDP_WITH_BDF
 #include "cpdp_bdf.cuh"
-#endif
 
 thread_local cpdp_emu_dim3 threadIdx;
 cpdp_emu_dim3 blockIdx, blockDim, gridDim;

@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 import lfsd_b200  # noqa: E402,F401
 from lfsd_b200 import synthetic  # noqa: E402
 from oracle import models  # noqa: E402
-from oracle.cpdp_oracle import Oracle, TIGHT  # noqa: E402
+from oracle.cpdp_oracle import Oracle, TIGHT, OracleIntegrationError  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -31,8 +31,15 @@ def run_problem(args):
     tg, X, U, Lam, info = orc.solve(x0, T, theta, return_info=True)
     out = dict(X=X, U=U, Lam=Lam, iters=info['iters'], J=info['J'], kkt=info['kkt'])
     for tag, back, fwd in (('asshipped', {'method': 'BDF'}, {}), ('rk45', {}, {}), ('tight', TIGHT, TIGHT)):
-        Xa, Ua, PW, cnt = orc.aux(tg, X, U, Lam, theta, back=back, fwd=fwd, return_counts=True)
+        try:
+            Xa, Ua, PW, cnt = orc.aux(tg, X, U, Lam, theta, back=back, fwd=fwd, return_counts=True)
+        except OracleIntegrationError as e:      # solve_ivp gave up (the reference would crash here): record it
+            print('FAILED VARIANT', kind, n_grid, np.asarray(theta), tag, e, flush=True)
+            n, m, r = orc.n, orc.m, orc.r
+            Xa = np.full((n_grid + 1, n * r), np.nan); Ua = np.full((n_grid + 1, m * r), np.nan)
+            PW = np.full((n_grid + 1, n * n + n * r), np.nan); cnt = dict(back_rhs=-1, fwd_rhs=-1)
         loss, dl = orc.loss_grad(taus, wp, tg, X, Xa)
+        out['ok_' + tag] = bool(np.isfinite(Xa).all())
         out['Xa_' + tag] = Xa; out['Ua_' + tag] = Ua; out['loss_' + tag] = loss; out['dl_' + tag] = dl
         out['cnt_' + tag] = np.array([cnt['back_rhs'], cnt['fwd_rhs']])
         if tag == 'asshipped':
@@ -68,9 +75,12 @@ def main():
     jobs['quad50'] = [('quadrotor', 50, qb['x0'][b], 1.0, qb['theta'], qb['goal'][b], qb['taus'], qb['wp'][b]) for b in range(6)]
     g = np.load(os.path.join(HERE, 'quad_run.npz'))
     jobs['quadkat'] = [('quadrotor', 25, g['ini_state'], 1.0, g['parameter_trace'][0], g['goal_position'], g['time_grid'], g['waypoints'])]
+    only = [a for a in sys.argv[1:] if not a.startswith('-')]
+    if only:
+        jobs = {k: v for k, v in jobs.items() if k in only}
     flat = [(name, j) for name, lst in jobs.items() for j in lst]
     with Pool(min(8, os.cpu_count())) as pool:
-        res = pool.map(run_problem, [j for _, j in flat])
+        res = pool.map(run_problem, [j for _, j in flat], chunksize=1)
     for name in jobs:
         rs = [r for (nm, _), r in zip(flat, res) if nm == name]
         js = jobs[name]

@@ -108,3 +108,54 @@ def test_reduce_tree_is_sharding_invariant(quad):
         assert np.array_equal(again, full)
     # and it is a correct sum
     assert np.allclose(full, np.concatenate([[loss.sum()], dth.sum(0)]), rtol=1e-12)
+
+
+def test_pendulum_bdf_asshipped_vs_oracle(pend):
+    """Mode 1 (scipy-BDF control logic with the closed-form Jacobian) against the oracle calling scipy's own BDF
+    exactly as the reference does (CPDP.py:333-336): same accepted steps, node tables equal to ~1e-9."""
+    from scipy.integrate import BDF
+    orc = Oracle(models.pendulum(), n_grid=10)
+    th = np.array([1.0, 0.5, 1.5])
+    tg, opt_sol = pend.cocSolver([0.0, 0.0], 1, th)
+    tgo, X, U, Lam = orc.solve([0.0, 0.0], 1.0, th)
+    pend.aux_mode = pend.MODE_BDF
+    pend.rtol_back, pend.atol_back, pend.rtol_fwd, pend.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
+    aux_sol = pend.auxSysSolver(tg, opt_sol, th)
+    assert pend.last_aux_status == 0
+    Xa, Ua, PW = orc.aux(tgo, X, U, Lam, th)          # as shipped: BDF backward, RK45 forward
+    got = aux_sol(tg)
+    assert _rel(got[:, :6], Xa) < 1e-8 and _rel(got[:, 6:], Ua) < 1e-8
+    # step / LU / rhs counters against scipy's BDF class driven interval by interval
+    from scipy.interpolate import interp1d
+    osol = interp1d(tgo, np.concatenate((X, U, Lam), axis=1), axis=0)
+
+    def rhs(t, y):
+        v = osol(t)
+        Pd, Wd = orc.riccati_rhs(v[:2], v[2:3], v[3:], th, y[:4].reshape(2, 2), y[4:].reshape(2, 3))
+        return np.concatenate((Pd.ravel(), Wd.ravel()))
+    nsteps = nlu = 0
+    y = PW[-1].copy()
+    for k in range(10, 0, -1):
+        s = BDF(rhs, tgo[k], y, tgo[k - 1])
+        while s.status == "running":
+            s.step()
+            nsteps += 1
+        nlu += s.nlu
+        y = s.y
+    c = pend.last_aux_counters
+    assert (c[1], c[4]) == (nsteps, nlu), (c, nsteps, nlu)
+
+
+def test_quad_k4_gradient_bdf_vs_stored_run(quad):
+    """KAT K4 through the emulated CUDA path in as-shipped mode: dL/dtheta(theta0) implied by the reference's stored
+    parameter_trace, tolerance 1e-5 relative (north_star); measured 1.8e-7."""
+    g = np.load(os.path.join(HERE, "golden", "quad_run.npz"))
+    quad.setIntegrator(n_grid=25)
+    quad.aux_mode = quad.MODE_BDF
+    quad.rtol_back, quad.atol_back, quad.rtol_fwd, quad.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
+    P, lr = g["parameter_trace"], float(g["learning_rate"])
+    sol = quad.cocSolverBatch(g["ini_state"].reshape(1, 13), 1.0, P[0], pdata=g["goal_position"].reshape(1, 3))
+    aux = quad.auxSysSolverBatch(sol, g["time_grid"], g["waypoints"].reshape(1, -1, 3), [0, 1, 2])
+    assert int(aux["aux_status"][0]) == 0
+    assert abs(aux["loss"][0] - g["loss_trace"][0]) / g["loss_trace"][0] < 1e-8
+    assert _rel(aux["dtheta"][0], (P[0] - P[1]) / lr) < 1e-5

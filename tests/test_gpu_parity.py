@@ -56,23 +56,30 @@ def _check_case(oc, fx, sel, modes):
     B = fx["x0"].shape[0]
     pd = fx["pdata"] if "pdata" in fx.files else None
     sol = oc.cocSolverBatch(fx["x0"], float(fx["T"]), fx["theta"], pdata=pd)
-    assert (_np(sol["status"]) == 1).all(), _np(sol["status"])
-    assert np.array_equal(_np(sol["iters"]), fx["iters"])
+    conv = fx["kkt"] < 1e-10                      # problems the oracle's Newton-KKT solve converged on
+    assert conv.any()
+    st = _np(sol["status"])
+    assert (st[conv] == 1).all(), st
+    assert (st[~conv] != 1).all(), st             # and the kernel agrees on the ones it did not
+    assert np.array_equal(_np(sol["iters"])[conv], fx["iters"][conv])
     for key in ("X", "U", "Lam"):
-        for b in range(B):
+        for b in np.flatnonzero(conv):
             assert _rel(_np(sol[key])[b], fx[key][b]) < TRAJ_RTOL, (key, b)
-    assert np.allclose(_np(sol["cost"]), fx["J"], rtol=1e-9)
+    assert np.allclose(_np(sol["cost"])[conv], fx["J"][conv], rtol=1e-9)
     for tag, mode, rb, ab, rf, af in modes:
         oc.aux_mode = mode
         oc.rtol_back, oc.atol_back, oc.rtol_fwd, oc.atol_fwd = rb, ab, rf, af
         taus = fx["taus"]
         aux = oc.auxSysSolverBatch(sol, taus, fx["wp"], sel)
-        assert (_np(aux["aux_status"]) == 0).all()
-        for b in range(B):
+        ok = fx["ok_" + tag] if ("ok_" + tag) in fx.files else np.ones(B, dtype=bool)
+        for b in np.flatnonzero(conv):
+            if not ok[b]:
+                continue                           # scipy gave up on this sweep (the reference would crash)
+            assert int(_np(aux["aux_status"])[b]) == 0, (tag, b)
             assert abs(_np(aux["loss"])[b] - fx["loss_" + tag][b]) <= 1e-8 * max(1.0, abs(fx["loss_" + tag][b]))
             assert _rel(_np(aux["dtheta"])[b], fx["dl_" + tag][b]) < GRAD_RTOL, (tag, b, _np(aux["dtheta"])[b], fx["dl_" + tag][b])
-            assert _rel(_np(aux["Xa"])[b], fx["Xa_" + tag][b]) < GRAD_RTOL
-            assert _rel(_np(aux["Ua"])[b], fx["Ua_" + tag][b]) < 10 * GRAD_RTOL
+            assert _rel(_np(aux["Xa"])[b], fx["Xa_" + tag][b]) < GRAD_RTOL, (tag, b)
+            assert _rel(_np(aux["Ua"])[b], fx["Ua_" + tag][b]) < 10 * GRAD_RTOL, (tag, b)
 
 
 def _modes(oc):
