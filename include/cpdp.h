@@ -36,7 +36,7 @@ int cpdp_num_counters(void);
 size_t cpdp_workspace_bytes(int B, int N, int S);
 
 /* Replaces COCSys.cocSolver (CPDP.py:92-198) for B problems: RK4 multiple-shooting NLP, all-zeros seed,
- * Newton-KKT with inertia correction and l1-merit line search.
+ * Newton-KKT with IPOPT's inertia correction and filter line search.
  *   x0[B][n]; theta[B][r] (theta_stride = r) or shared theta[r] (theta_stride = 0); T horizon;
  *   tol: KKT tolerance; max_iter: Newton iteration cap;
  *   rounds > 0: launch exactly that many Newton rounds with no host synchronisation (CUDA-graph capturable);

@@ -43,7 +43,9 @@ static WsLayout ws_carve(char* base, int B, int N, int S) {
     a.dX = takeD(BN1 * NX);
     a.dU = takeD(BN * NU);
     a.lamn = takeD(BN1 * NX);
-    a.nu = takeD(B);
+    a.th_init = takeD(B);
+    a.filt = takeD((size_t)B * FILTER_CAP * 2);
+    a.nfilt = takeI(B);
     a.dlast = takeD(B);
     a.J = takeD(B);
     a.kkt = takeD(B);
@@ -95,7 +97,7 @@ CPDP_API int cpdp_solve(void* ws, size_t ws_bytes, int B, int N, int S, double T
     WsLayout w = ws_carve((char*)ws, B, N, S);
     if (w.bytes > ws_bytes) return -3;
     SolveArgs a = w.sa;
-    a.B = B; a.N = N; a.S = S; a.T = T; a.tol = tol; a.max_iter = max_iter;
+    a.B = B; a.N = N; a.S = S; a.T = T; a.tol = tol; a.max_iter = (max_iter < FILTER_CAP) ? max_iter : FILTER_CAP - 1;
     if (NQ > 0 && !pdata) return -8;
     a.x0 = x0; a.theta = theta; a.theta_stride = theta_stride; a.pdata = pdata;
     a.X = X; a.U = U; a.Lam = Lam; a.status = status; a.iters = iters;

@@ -19,6 +19,8 @@ constexpr int NP = Model::NP;
 constexpr int NZ = NX + NU;
 constexpr int NQ = Model::NQ;          // per-problem constants (not learnable)
 
+constexpr int FILTER_CAP = 256;        // filter entries per problem (one is added per h-type iteration at most)
+
 enum Status { ST_RUNNING = 0, ST_CONVERGED = 1, ST_MAXITER = 2, ST_LINESEARCH = 3, ST_NUMERIC = 4 };
 
 // ------------------------------------------------------------------------------------------------
@@ -54,7 +56,9 @@ struct SolveArgs {
     double* dX;                  // [B][N+1][NX]
     double* dU;                  // [B][N][NU]
     double* lamn;                // [B][N+1][NX]
-    double* nu;                  // [B]  merit penalty
+    double* th_init;             // [B]  max(1, theta(x0)): scale of the filter's theta_min / theta_max
+    double* filt;                // [B][FILTER_CAP][2]  filter corners (theta, phi)
+    int* nfilt;                  // [B]  filter entries in use
     double* dlast;               // [B]  last inertia-correction delta
     double* J;                   // [B]  objective at the current iterate
     double* kkt;                 // [B]  KKT error at the current iterate
@@ -346,7 +350,7 @@ CPDP_HD void chol_solve(const double* L, double* b) {
 //  1. KKT error of the current iterate (stop test, IPOPT-style: max(|grad L|, |g|)).
 //  2. Newton step of the equality-constrained NLP by the Riccati recursion on the stage-wise KKT system, with
 //     IPOPT's inertia-correction schedule when some Quu block is not positive definite.
-//  3. l1-merit backtracking line search (one thread per interval re-integrates the RK4 map).
+//  3. IPOPT filter line search (one thread per interval re-integrates the RK4 map).
 //  4. Primal / dual update.
 // ------------------------------------------------------------------------------------------------
 constexpr int NEWTON_THREADS = 64;
@@ -550,25 +554,32 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
     }
     __syncthreads();
 
-    // ---- merit function data
-    double lmax = 0.0, gd = 0.0;
-    for (int i = tid; i < (N + 1) * NX; i += nt) lmax = fmax(lmax, fabs(lamn[i]));
+    // ---- directional derivative of the objective along the step
+    double gd = 0.0, bad = 0.0;
+    for (int i = tid; i < (N + 1) * NX; i += nt) if (!(fabs(lamn[i]) < 1e300)) bad = 1.0;
     for (int k = tid; k < N; k += nt) {
         const double* g = a.gq + (ib + k) * NZ;
         for (int i = 0; i < NX; ++i) gd += g[i] * dX[(size_t)k * NX + i];
         for (int i = 0; i < NU; ++i) gd += g[NX + i] * dU[(size_t)k * NU + i];
     }
     for (int i = tid; i < NX; i += nt) gd += s_hx[i] * dX[(size_t)N * NX + i];
-    lmax = block_reduce(lmax, red, true);
+    bad = block_reduce(bad, red, true);
     gd = block_reduce(gd, red, false);
-    if (!(lmax == lmax) || !(gd == gd)) { if (tid == 0) a.status[b] = ST_NUMERIC; return; }
-    const double nu = fmax(a.nu[b], 1.1 * lmax);
-    const double phi0 = J0 + nu * g1;
-    const double Dphi = gd - nu * g1;
+    if (bad != 0.0 || !(gd == gd)) { if (tid == 0) a.status[b] = ST_NUMERIC; return; }
 
-    // ---- backtracking line search on the l1 merit function
+    // ---- IPOPT filter line search (Waechter & Biegler 2006, Sec. 2.3; phi = J, theta = |g|_1, default constants
+    //      gamma_theta 1e-5, gamma_phi 1e-8, delta 1, s_theta 1.1, s_phi 2.3, eta_phi 1e-8; no second-order
+    //      correction, no restoration phase).  One thread per interval re-integrates the RK4 map at each trial point.
+    const double th0 = g1;
+    if (it == 0 && tid == 0) a.th_init[b] = fmax(1.0, th0);
+    __syncthreads();
+    const double theta_min = 1e-4 * a.th_init[b], theta_max = 1e4 * a.th_init[b];
+    const int nf = a.nfilt[b];
+    const double* filt = a.filt + (size_t)b * FILTER_CAP * 2;
+    const double sw_rhs = pow(th0, 1.1);
+    const double sw_lhs = (gd < 0) ? pow(-gd, 2.3) : 0.0;
     double alpha = 1.0;
-    bool ok = false;
+    bool ok = false, ftype = false;
     for (int ls = 0; ls <= 30; ++ls) {
         double Jt = 0.0, gt = 0.0;
         for (int k = tid; k <= N; k += nt) {
@@ -590,11 +601,26 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
         }
         Jt = block_reduce(Jt, red, false);
         gt = block_reduce(gt, red, false);
-        const double phit = Jt + nu * gt;
-        if (phit == phit && fabs(phit) < 1e300 && phit <= phi0 + 1e-4 * alpha * Dphi) { ok = true; break; }
+        bool acc = (Jt == Jt) && (gt == gt) && fabs(Jt) < 1e300 && gt <= theta_max;
+        for (int e = 0; acc && e < nf; ++e) if (gt >= filt[2 * e] && Jt >= filt[2 * e + 1]) acc = false;
+        if (acc) {
+            const bool switching = (gd < 0) && (alpha * sw_lhs > sw_rhs);
+            if (switching && th0 <= theta_min) {
+                acc = (Jt <= J0 + 1e-8 * alpha * gd);
+                ftype = acc;
+            } else {
+                acc = (gt <= (1 - 1e-5) * th0) || (Jt <= J0 - 1e-8 * th0);
+            }
+        }
+        if (acc) { ok = true; break; }
         alpha *= 0.5;
     }
     if (!ok) { if (tid == 0) a.status[b] = ST_LINESEARCH; return; }
+    if (!ftype && tid == 0 && nf < FILTER_CAP) {
+        a.filt[((size_t)b * FILTER_CAP + nf) * 2] = (1 - 1e-5) * th0;
+        a.filt[((size_t)b * FILTER_CAP + nf) * 2 + 1] = J0 - 1e-8 * th0;
+        a.nfilt[b] = nf + 1;
+    }
 
     // ---- update
     for (int i = tid; i < (N + 1) * NX; i += nt) {
@@ -602,7 +628,7 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
         Lam[i] += alpha * (lamn[i] - Lam[i]);
     }
     for (int i = tid; i < N * NU; i += nt) U[i] += alpha * dU[i];
-    if (tid == 0) { a.nu[b] = nu; a.iters[b] = it + 1; }
+    if (tid == 0) a.iters[b] = it + 1;
 }
 
 CPDP_GLOBAL void __launch_bounds__(NEWTON_THREADS) k_newton_step(SolveArgs a) {
@@ -620,7 +646,7 @@ CPDP_GLOBAL void k_solve_init(SolveArgs a) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot * NX; i += gs) { a.X[i] = 0.0; a.Lam[i] = 0.0; }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot * NU; i += gs) a.U[i] = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)a.B; i += gs) {
-        a.status[i] = ST_RUNNING; a.iters[i] = 0; a.nu[i] = 0.0; a.dlast[i] = 0.0; a.J[i] = 0.0; a.kkt[i] = 0.0;
+        a.status[i] = ST_RUNNING; a.iters[i] = 0; a.th_init[i] = 1.0; a.nfilt[i] = 0; a.dlast[i] = 0.0; a.J[i] = 0.0; a.kkt[i] = 0.0;
     }
 }
 

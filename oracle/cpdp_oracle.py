@@ -10,8 +10,9 @@ A numpy/scipy restatement of the reference algorithm, following it step for step
                        the casadi wheel's bundled build) is replaced by its published algorithm restricted to
                        this problem class (no inequalities => no barrier): full-space Newton on the KKT system
                        with exact Lagrangian Hessian, IPOPT's inertia-correction schedule (Waechter & Biegler
-                       2006, Alg. IC: 1e-4, x100 first time, x8 afterwards, /3 on re-entry) and a backtracking
-                       l1-merit line search.  Pinned by the reference's stored run (tests/golden, KAT K2/K3).
+                       2006, Alg. IC: 1e-4, x100 first time, x8 afterwards, /3 on re-entry) and IPOPT's filter
+                       line search (same paper, Sec. 2.3, default constants; no second-order correction, no
+                       restoration phase).  Pinned by the reference's stored run (tests/golden, KAT K2/K3).
   * ``aux_asshipped``← ``COCSys.auxSysSolver``   /root/reference/CPDP/CPDP.py:301-381, RHS formulas :253-298,
                        derivative set :201-248.  Calls the installed ``scipy.integrate.solve_ivp`` exactly as the
                        reference does (BDF backward / default RK45 forward, default tolerances, one call per grid
@@ -197,7 +198,8 @@ class Oracle:
             J += self.fn.term(wv[ox(N):ox(N) + n], th, self.pd)[0]
             return J, g
 
-        nu = 0.0
+        filt = []                 # IPOPT filter: list of (theta, phi) corners
+        theta_min = theta_max = None
         delta_last = 0.0
         info = dict(iters=0, status='max_iter', reg=[], alphas=[])
         for it in range(max_iter + 1):
@@ -253,28 +255,46 @@ class Oracle:
             info['reg'].append(delta)
             sol = np.linalg.solve(K, -np.concatenate([gradJ, g]))
             d, lam_new = sol[:nw], sol[nw:]
-            # ---- l1 merit line search
-            nu = max(nu, 1.1 * np.abs(lam_new).max())
-            g1 = np.abs(g).sum()
-            phi0 = J + nu * g1
-            Dphi = gradJ @ d - nu * g1
+            # ---- IPOPT filter line search (Waechter & Biegler 2006, Sec. 2.3; no barrier term: phi = J,
+            #      theta = |g|_1; constants = IPOPT defaults gamma_theta 1e-5, gamma_phi 1e-8, delta 1, s_theta 1.1,
+            #      s_phi 2.3, eta_phi 1e-8, theta_min/max = 1e-4/1e4 * max(1, theta(x0)); no second-order correction
+            #      and no restoration phase: more than 30 halvings -> 'linesearch_fail')
+            th0 = np.abs(g).sum()
+            if theta_min is None:
+                theta_min = 1e-4 * max(1.0, th0)
+                theta_max = 1e4 * max(1.0, th0)
+            gd = gradJ @ d
             alpha = 1.0
-            while True:
+            accepted = ftype = False
+            for _ls in range(31):
                 try:
                     with np.errstate(all='ignore'):
                         Jt, gt = evaluate(w + alpha * d)
-                    phit = Jt + nu * np.abs(gt).sum()
+                    tht = np.abs(gt).sum()
                 except (ValueError, OverflowError, FloatingPointError):   # e.g. math.cos(inf) at a wild trial point
-                    phit = np.inf
-                if np.isfinite(phit) and phit <= phi0 + 1e-4 * alpha * Dphi:
+                    Jt = tht = np.inf
+                ok = np.isfinite(Jt) and np.isfinite(tht) and tht <= theta_max
+                if ok:
+                    for (tf, pf) in filt:
+                        if tht >= tf and Jt >= pf:
+                            ok = False
+                            break
+                if ok:
+                    switching = gd < 0 and alpha * (-gd) ** 2.3 > th0 ** 1.1
+                    if switching and th0 <= theta_min:
+                        if Jt <= J + 1e-8 * alpha * gd:
+                            accepted = ftype = True
+                    elif tht <= (1 - 1e-5) * th0 or Jt <= J - 1e-8 * th0:
+                        accepted = True
+                if accepted:
                     break
                 alpha *= 0.5
-                if alpha < 2.0 ** -30:
-                    info['status'] = 'linesearch_fail'
-                    break
-            info['alphas'].append(alpha)
-            if info['status'] == 'linesearch_fail':
+            if not accepted:
+                info['status'] = 'linesearch_fail'
                 break
+            if not ftype:
+                filt.append(((1 - 1e-5) * th0, J - 1e-8 * th0))
+            info['alphas'].append(alpha)
             w = w + alpha * d
             lam = lam + alpha * (lam_new - lam)
             info['iters'] = it + 1

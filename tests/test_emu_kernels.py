@@ -67,7 +67,7 @@ def test_quad_k2_stored_optimum(quad):
     quad.setIntegrator(n_grid=25)
     sol = quad.cocSolverBatch(g["ini_state"].reshape(1, 13), 1.0, g["parameter_trace"][-1],
                               pdata=g["goal_position"].reshape(1, 3))
-    assert int(sol["status"][0]) == 1 and int(sol["iters"][0]) == 7
+    assert int(sol["status"][0]) == 1 and int(sol["iters"][0]) <= 7
     assert np.abs(sol["X"][0] - g["opt_state_traj"][::4]).max() < 1e-10
     assert np.abs(sol["U"][0] - g["opt_control_traj"][::4]).max() < 1e-10
     assert np.array_equal(sol["U"][0][-1], sol["U"][0][-2])          # CPDP.py:191

@@ -23,9 +23,11 @@ def _fx(name):
     return np.load(p)
 
 
-def _rel(a, b):
+def _rel(a, b, floor=1e-300):
+    """relative l2 error; `floor` is the smallest reference norm treated as non-zero (a problem whose waypoints lie
+    exactly on its own optimum has loss 0 and gradient 0 in the oracle and O(1e-15) on the GPU)."""
     a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
-    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), floor)
 
 
 def _np(t):
@@ -77,7 +79,7 @@ def _check_case(oc, fx, sel, modes):
                 continue                           # scipy gave up on this sweep (the reference would crash)
             assert int(_np(aux["aux_status"])[b]) == 0, (tag, b)
             assert abs(_np(aux["loss"])[b] - fx["loss_" + tag][b]) <= 1e-8 * max(1.0, abs(fx["loss_" + tag][b]))
-            assert _rel(_np(aux["dtheta"])[b], fx["dl_" + tag][b]) < GRAD_RTOL, (tag, b, _np(aux["dtheta"])[b], fx["dl_" + tag][b])
+            assert _rel(_np(aux["dtheta"])[b], fx["dl_" + tag][b], floor=1e-6) < GRAD_RTOL, (tag, b, _np(aux["dtheta"])[b], fx["dl_" + tag][b])
             assert _rel(_np(aux["Xa"])[b], fx["Xa_" + tag][b]) < GRAD_RTOL, (tag, b)
             assert _rel(_np(aux["Ua"])[b], fx["Ua_" + tag][b]) < 10 * GRAD_RTOL, (tag, b)
 
