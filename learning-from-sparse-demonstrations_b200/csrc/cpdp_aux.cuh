@@ -114,6 +114,10 @@ struct AuxShared {
     double* Yp;       // [NU*NX]
     double* Z;        // [NU*NP]
     int* ti; int* tj; // [NT]
+    // sparsity tables of fx, fu, fe copied to shared memory (CSR: rowptr/colidx, CSC: colptr/rowidx)
+    const int* fx_rowptr; const int* fx_colidx; const int* fx_colptr; const int* fx_rowidx;
+    const int* fu_rowptr; const int* fu_colidx; const int* fu_colptr; const int* fu_rowidx;
+    const int* fe_colptr; const int* fe_rowidx;
     // forward only
     double* PWt;      // [NSLOT][NYR]
     double* HY;       // [NSLOT][NU*NX]
@@ -162,16 +166,16 @@ CPDP_D void riccati_rhs(const AuxShared& s, const double* M, const double* yin, 
         if (i < NU * NX) {
             const int a = i / NX, j = i % NX;
             double acc = Hxu[j * NU + a];
-            for (int p = Model::FU_colptr(a); p < Model::FU_colptr(a + 1); ++p) {
-                const int r_ = Model::FU_rowidx(p);
+            for (int p = s.fu_colptr[a]; p < s.fu_colptr[a + 1]; ++p) {
+                const int r_ = s.fu_rowidx[p];
                 acc += fu[r_ * NU + a] * s.P[r_ * NX + j];
             }
             s.Y[i] = acc;
         } else {
             const int q = i - NU * NX, a = q / NP, k = q % NP;
             double acc = Hue[a * NP + k];
-            for (int p = Model::FU_colptr(a); p < Model::FU_colptr(a + 1); ++p) {
-                const int r_ = Model::FU_rowidx(p);
+            for (int p = s.fu_colptr[a]; p < s.fu_colptr[a + 1]; ++p) {
+                const int r_ = s.fu_rowidx[p];
                 acc += fu[r_ * NU + a] * Wm[r_ * NP + k];
             }
             s.Z[q] = acc;
@@ -189,12 +193,12 @@ CPDP_D void riccati_rhs(const AuxShared& s, const double* M, const double* yin, 
         if (q < NT) {
             const int i = s.ti[q], j = s.tj[q];
             double acc = Hxx[i * NX + j];
-            for (int p = Model::FX_colptr(i); p < Model::FX_colptr(i + 1); ++p) {
-                const int a = Model::FX_rowidx(p);
+            for (int p = s.fx_colptr[i]; p < s.fx_colptr[i + 1]; ++p) {
+                const int a = s.fx_rowidx[p];
                 acc += fx[a * NX + i] * s.P[a * NX + j];
             }
-            for (int p = Model::FX_colptr(j); p < Model::FX_colptr(j + 1); ++p) {
-                const int a = Model::FX_rowidx(p);
+            for (int p = s.fx_colptr[j]; p < s.fx_colptr[j + 1]; ++p) {
+                const int a = s.fx_rowidx[p];
                 acc += s.P[i * NX + a] * fx[a * NX + j];
             }
             // symmetric evaluation of Y' Hinv Y: average of (i,j) and (j,i) orderings is not needed because
@@ -205,12 +209,12 @@ CPDP_D void riccati_rhs(const AuxShared& s, const double* M, const double* yin, 
         } else {
             const int e = q - NT, i = e / NP, k = e % NP;
             double acc = -Hxe[i * NP + k];
-            for (int p = Model::FX_colptr(i); p < Model::FX_colptr(i + 1); ++p) {
-                const int a = Model::FX_rowidx(p);
+            for (int p = s.fx_colptr[i]; p < s.fx_colptr[i + 1]; ++p) {
+                const int a = s.fx_rowidx[p];
                 acc -= fx[a * NX + i] * Wm[a * NP + k];
             }
-            for (int p = Model::FE_colptr(k); p < Model::FE_colptr(k + 1); ++p) {
-                const int a = Model::FE_rowidx(p);
+            for (int p = s.fe_colptr[k]; p < s.fe_colptr[k + 1]; ++p) {
+                const int a = s.fe_rowidx[p];
                 acc -= s.P[i * NX + a] * fe[a * NP + k];
             }
             for (int a = 0; a < NU; ++a) acc += s.Yp[a * NX + i] * s.Z[a * NP + k];
@@ -239,12 +243,12 @@ CPDP_D void forward_rhs(const AuxShared& s, int slot, const double* Xin, double*
     for (int q = tid; q < NYF; q += nt) {
         const int i = q / NP, k = q % NP;
         double acc = fe[q];
-        for (int p = Model::FX_rowptr(i); p < Model::FX_rowptr(i + 1); ++p) {
-            const int a = Model::FX_colidx(p);
+        for (int p = s.fx_rowptr[i]; p < s.fx_rowptr[i + 1]; ++p) {
+            const int a = s.fx_colidx[p];
             acc += fx[i * NX + a] * Xin[a * NP + k];
         }
-        for (int p = Model::FU_rowptr(i); p < Model::FU_rowptr(i + 1); ++p) {
-            const int a = Model::FU_colidx(p);
+        for (int p = s.fu_rowptr[i]; p < s.fu_rowptr[i + 1]; ++p) {
+            const int a = s.fu_colidx[p];
             acc += fu[i * NU + a] * s.Uc[a * NP + k];
         }
         Xdot[q] = acc;
@@ -281,16 +285,16 @@ CPDP_D bool aux_prepare(const AuxShared& s, const AuxProblem& p, const double* t
             if (i < NU * NX) {
                 const int a = i / NX, j = i % NX;
                 double acc = M[Model::PMP_HXU + j * NU + a];
-                for (int pp = Model::FU_colptr(a); pp < Model::FU_colptr(a + 1); ++pp) {
-                    const int r_ = Model::FU_rowidx(pp);
+                for (int pp = s.fu_colptr[a]; pp < s.fu_colptr[a + 1]; ++pp) {
+                    const int r_ = s.fu_rowidx[pp];
                     acc += fu[r_ * NU + a] * PWt[r_ <= j ? tri(r_, j) : tri(j, r_)];
                 }
                 s.HY[(size_t)sl * NU * NX + i] = acc;
             } else {
                 const int e = i - NU * NX, a = e / NP, k = e % NP;
                 double acc = M[Model::PMP_HUE + a * NP + k];
-                for (int pp = Model::FU_colptr(a); pp < Model::FU_colptr(a + 1); ++pp) {
-                    const int r_ = Model::FU_rowidx(pp);
+                for (int pp = s.fu_colptr[a]; pp < s.fu_colptr[a + 1]; ++pp) {
+                    const int r_ = s.fu_rowidx[pp];
                     acc += fu[r_ * NU + a] * PWt[NT + r_ * NP + k];
                 }
                 s.HZ[(size_t)sl * NU * NP + e] = acc;
@@ -443,6 +447,25 @@ constexpr int FWD_SMEM_DOUBLES = NSLOT * MSZ + NSLOT * (2 * NX + NU) + (AUX_THRE
 
 CPDP_D double* carve(double*& ptr, int n) { double* r_ = ptr; ptr += n; return r_; }
 
+// shared-memory copy of the model's static sparsity tables (divergent lookups are cheap there)
+constexpr int SPTAB_INTS = 2 * (NX + 1) + 2 * Model::FX_nnz + (NX + 1) + (NU + 1) + 2 * Model::FU_nnz + (NP + 1) + Model::FE_nnz + 8;
+CPDP_D void aux_tables(AuxShared& s, int* tab) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int* p = tab;
+    int* fx_rowptr = p; p += NX + 1; int* fx_colidx = p; p += Model::FX_nnz; int* fx_colptr = p; p += NX + 1; int* fx_rowidx = p; p += Model::FX_nnz;
+    int* fu_rowptr = p; p += NX + 1; int* fu_colidx = p; p += Model::FU_nnz; int* fu_colptr = p; p += NU + 1; int* fu_rowidx = p; p += Model::FU_nnz;
+    int* fe_colptr = p; p += NP + 1; int* fe_rowidx = p; p += Model::FE_nnz;
+    for (int i = tid; i <= NX; i += nt) { fx_rowptr[i] = Model::FX_rowptr(i); fx_colptr[i] = Model::FX_colptr(i); fu_rowptr[i] = Model::FU_rowptr(i); }
+    for (int i = tid; i <= NU; i += nt) fu_colptr[i] = Model::FU_colptr(i);
+    for (int i = tid; i <= NP; i += nt) fe_colptr[i] = Model::FE_colptr(i);
+    for (int i = tid; i < Model::FX_nnz; i += nt) { fx_colidx[i] = Model::FX_colidx(i); fx_rowidx[i] = Model::FX_rowidx(i); }
+    for (int i = tid; i < Model::FU_nnz; i += nt) { fu_colidx[i] = Model::FU_colidx(i); fu_rowidx[i] = Model::FU_rowidx(i); }
+    for (int i = tid; i < Model::FE_nnz; i += nt) fe_rowidx[i] = Model::FE_rowidx(i);
+    s.fx_rowptr = fx_rowptr; s.fx_colidx = fx_colidx; s.fx_colptr = fx_colptr; s.fx_rowidx = fx_rowidx;
+    s.fu_rowptr = fu_rowptr; s.fu_colidx = fu_colidx; s.fu_colptr = fu_colptr; s.fu_rowidx = fu_rowidx;
+    s.fe_colptr = fe_colptr; s.fe_rowidx = fe_rowidx;
+}
+
 CPDP_D void aux_shared_common(AuxShared& s, double*& ptr, int* ti, int* tj) {
     s.M = carve(ptr, NSLOT * MSZ);
     s.xul = carve(ptr, NSLOT * (2 * NX + NU));
@@ -466,7 +489,7 @@ CPDP_D void aux_shared_common(AuxShared& s, double*& ptr, int* ti, int* tj) {
 // ------------------------------------------------------------------------------------------------
 CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
     CPDP_DYN_SMEM(smem);
-    CPDP_SHARED int s_ti[NT], s_tj[NT];
+    CPDP_SHARED int s_ti[NT], s_tj[NT], s_tab[SPTAB_INTS];
     CPDP_SHARED double s_hxx[NX * NX], s_hxe[NX * NP];
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     // The reference never looks at IPOPT's return status (CPDP.py:183); here trajectories that are not a solution
@@ -478,6 +501,7 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
     double* ptr = smem;
     AuxShared s;
     aux_shared_common(s, ptr, s_ti, s_tj);
+    aux_tables(s, s_tab);
     double* y = carve(ptr, NYR); double* yn = carve(ptr, NYR); double* ys = carve(ptr, NYR);
     double* K = carve(ptr, 7 * NYR); double* tms = carve(ptr, 8);
     const int N = a.N;
@@ -516,7 +540,7 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
 // ------------------------------------------------------------------------------------------------
 CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_aux_forward(AuxArgs a) {
     CPDP_DYN_SMEM(smem);
-    CPDP_SHARED int s_ti[NT], s_tj[NT];
+    CPDP_SHARED int s_ti[NT], s_tj[NT], s_tab[SPTAB_INTS];
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     if (a.aux_status[b] != 0) {
         if (tid == 0) a.loss[b] = 0.0;
@@ -526,6 +550,7 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_aux_forward(AuxArgs a) {
     double* ptr = smem;
     AuxShared s;
     aux_shared_common(s, ptr, s_ti, s_tj);
+    aux_tables(s, s_tab);
     s.PWt = carve(ptr, NSLOT * NYR); s.HY = carve(ptr, NSLOT * NU * NX); s.HZ = carve(ptr, NSLOT * NU * NP);
     s.Uc = carve(ptr, NU * NP);
     double* y = carve(ptr, NYF); double* yn = carve(ptr, NYF); double* ys = carve(ptr, NYF);

@@ -28,6 +28,7 @@ constexpr int BDF_THREADS = 128;
 constexpr int BDF_MAX_ORDER = 5;
 constexpr int BDF_NEWTON_MAXITER = 4;
 constexpr int BDF_NROWS = BDF_MAX_ORDER + 3;
+constexpr int BDF_GJ_NP = ((NT + 15) / 16) * 16 > ((NT + 7) / 8) * 8 ? ((NT + 15) / 16) * 16 : ((NT + 7) / 8) * 8;   // = GJ_NP below
 
 struct BdfShared {
     double* G;      // [NT*NT]  LU of the packed operator X -> X + c (L X + X L')
@@ -40,7 +41,10 @@ struct BdfShared {
     double* D;      // [BDF_NROWS][NYR]
     double* ypred; double* scale; double* psi; double* d; double* y; double* f; double* dy;
     double* RU;     // [6*6]
-    int* piv;       // [NT]
+    double* Winv;   // [NX*NX]  inverse of I + c L
+    double* gjbuf;  // [2*GJ_NP] pivot column / pivot row exchange of the Gauss-Jordan steps
+    double* tmp;    // [NYR]    scratch of bdf_solve
+    int* piv;       // [3*GJ_NP] used flags, perm, kidx
     int* wpiv;      // [NX]
 };
 
@@ -108,26 +112,6 @@ CPDP_D bool block_lu(double* A, const int n, int* piv, double* red) {
     return true;
 }
 
-// Solve A x = b in place (A from block_lu), single right-hand side in shared memory, whole CTA.
-CPDP_D void block_lu_solve(const double* A, const int n, const int* piv, double* b) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    __syncthreads();
-    if (tid == 0) for (int k = 0; k < n; ++k) { const int p = piv[k]; if (p != k) { const double t = b[k]; b[k] = b[p]; b[p] = t; } }
-    __syncthreads();
-    for (int k = 0; k < n - 1; ++k) {
-        const double bk = b[k];
-        for (int i = k + 1 + tid; i < n; i += nt) b[i] -= A[i * n + k] * bk;
-        __syncthreads();
-    }
-    for (int k = n - 1; k >= 0; --k) {
-        if (tid == 0) b[k] /= A[k * n + k];
-        __syncthreads();
-        const double bk = b[k];
-        for (int i = tid; i < k; i += nt) b[i] -= A[i * n + k] * bk;
-        __syncthreads();
-    }
-}
-
 // Closed-form Jacobian data at (PMP matrices M, packed state yJ):  L = A' - P R,  C = R W - r_
 // with A = fx - fu Huu^{-1} Hxu', R = fu Huu^{-1} fu', r_ = fe - fu Huu^{-1} Hue  (CPDP.py:262-270).
 CPDP_D void bdf_jacobian(const AuxShared& s, const BdfShared& bs, const double* M, const double* yJ) {
@@ -171,53 +155,183 @@ CPDP_D void bdf_jacobian(const AuxShared& s, const BdfShared& bs, const double* 
     __syncthreads();
 }
 
-// Assemble and factorise I - cJ in its structured form.
+// ------------------------------------------------------------------------------------------------
+// Inverse of the packed Newton operator  X -> X + c (L X + X L')  (NT x NT, NT = n(n+1)/2) held in REGISTERS.
+// The CTA is an 8 x 16 grid of threads (thread t: row group tr = t % 8, column group tc = t / 8); element (i, j)
+// lives in thread (i % 8, j % 16), local slot (i / 8, j / 16).  In-place Gauss-Jordan with implicit partial pivoting:
+// rows are never swapped, the pivot row of step k is only marked as used.  Per step the pivot column and the pivot row
+// travel through shared memory (2 barriers), the rank-1 update runs on register tiles (FP64-pipe bound instead of
+// shared-memory bound).  The result is written to shared memory with both permutations folded in, so that a Newton
+// solve is one plain matrix-vector product.
+// ------------------------------------------------------------------------------------------------
+constexpr int GJ_TR = 8, GJ_TC = 16;
+constexpr int GJ_RT = (NT + GJ_TR - 1) / GJ_TR;        // rows per thread
+constexpr int GJ_CT = (NT + GJ_TC - 1) / GJ_TC;        // columns per thread
+constexpr int GJ_NP = GJ_RT * GJ_TR > GJ_CT * GJ_TC ? GJ_RT * GJ_TR : GJ_CT * GJ_TC;   // padded extent
+static_assert(BDF_THREADS == GJ_TR * GJ_TC, "thread grid of the Gauss-Jordan tiles");
+static_assert(GJ_NP == BDF_GJ_NP, "padded extent");
+
+// coefficient of X_uv (u <= v) in row (i <= j) of  X + c (L X + X L')  for symmetric X
+CPDP_D double gj_entry(const double* Lm, const double c, int i, int j, int u, int v) {
+    double acc = 0.0;
+    if (j == v) acc += Lm[i * NX + u];
+    if (j == u && u != v) acc += Lm[i * NX + v];
+    if (i == u) acc += Lm[j * NX + v];
+    if (i == v && u != v) acc += Lm[j * NX + u];
+    return ((i == u && j == v) ? 1.0 : 0.0) + c * acc;
+}
+
+// arg-max of |col[i]| over rows that are not used yet; every thread returns the same (p, value); ties -> smallest i
+CPDP_D int gj_pivot(const double* col, const int* used, double& pval) {
+#ifdef __CUDACC__
+    const int lane = threadIdx.x & 31;
+    double best = -1.0; int bi = 0x7fffffff;
+    for (int i = lane; i < NT; i += 32) {
+        const double v = used[i] ? -1.0 : fabs(col[i]);
+        if (v > best) { best = v; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double x = __shfl_xor_sync(0xffffffffu, best, o);
+        const int xi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (x > best || (x == best && xi < bi)) { best = x; bi = xi; }
+    }
+#else
+    double best = -1.0; int bi = 0x7fffffff;
+    for (int i = 0; i < NT; ++i) {
+        const double v = used[i] ? -1.0 : fabs(col[i]);
+        if (v > best) { best = v; bi = i; }
+    }
+#endif
+    pval = best;
+    return bi;
+}
+
+// Assemble and invert I - cJ in its structured form: bs.G <- inverse of the packed operator (row-major NT x NT),
+// bs.Wl <- inverse of I + c L.
 CPDP_D bool bdf_factor(const AuxShared& s, const BdfShared& bs, const double c) {
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int tr = tid % GJ_TR, tc = tid / GJ_TR;
+    double* colbuf = bs.gjbuf;                  // [GJ_NP] pivot column of the current step
+    double* rowbuf = bs.gjbuf + GJ_NP;          // [GJ_NP] pivot row of the current step
+    int* used = bs.piv;                         // [GJ_NP] row already used as a pivot
+    int* perm = bs.piv + GJ_NP;                 // [NT]    perm[k] = pivot row of step k
+    int* kidx = bs.piv + 2 * GJ_NP;             // [GJ_NP] kidx[i] = step at which row i was the pivot
+    double A[GJ_RT][GJ_CT];
     __syncthreads();
-    for (int i = tid; i < NT * NT; i += nt) bs.G[i] = 0.0;
-    for (int i = tid; i < NX * NX; i += nt) bs.Wl[i] = ((i / NX == i % NX) ? 1.0 : 0.0) + c * bs.Lm[i];
-    __syncthreads();
-    for (int q = tid; q < NT; q += nt) {
-        const int i = s.ti[q], j = s.tj[q];
-        double* row = bs.G + (size_t)q * NT;
-        row[q] += 1.0;
-        for (int a = 0; a < NX; ++a) {
-            row[a <= j ? tri(a, j) : tri(j, a)] += c * bs.Lm[i * NX + a];      // (L X)_ij
-            row[i <= a ? tri(i, a) : tri(a, i)] += c * bs.Lm[j * NX + a];      // (X L')_ij
+    // ---- assemble the register tiles; publish column 0
+#pragma unroll
+    for (int a = 0; a < GJ_RT; ++a) {
+        const int q = tr + GJ_TR * a;
+#pragma unroll
+        for (int cc = 0; cc < GJ_CT; ++cc) {
+            const int col = tc + GJ_TC * cc;
+            double v = 0.0;
+            if (q < NT && col < NT) v = gj_entry(bs.Lm, c, s.ti[q], s.tj[q], s.ti[col], s.tj[col]);
+            A[a][cc] = v;
+            if (col == 0) colbuf[q] = v;
         }
     }
+    for (int i = tid; i < GJ_NP; i += nt) { used[i] = (i >= NT) ? 1 : 0; rowbuf[i] = 0.0; }
+    for (int i = tid; i < NX * NX; i += nt) bs.Wl[i] = ((i / NX == i % NX) ? 1.0 : 0.0) + c * bs.Lm[i];
     __syncthreads();
-    if (!block_lu(bs.G, NT, bs.piv, s.red)) return false;
+    bool singular = false;
+    for (int k = 0; k < NT; ++k) {
+        double pval;
+        const int p = gj_pivot(colbuf, used, pval);           // every thread computes the same pivot
+        if (!(pval > 0.0)) { singular = true; break; }
+        const int ap = p / GJ_TR;
+        const bool rowowner = (tr == p % GJ_TR);
+        if (rowowner) {
+#pragma unroll
+            for (int a = 0; a < GJ_RT; ++a) if (a == ap) {
+#pragma unroll
+                for (int cc = 0; cc < GJ_CT; ++cc) rowbuf[tc + GJ_TC * cc] = A[a][cc];
+            }
+        }
+        double f[GJ_RT];
+#pragma unroll
+        for (int a = 0; a < GJ_RT; ++a) f[a] = colbuf[tr + GJ_TR * a];
+        const double inv = 1.0 / colbuf[p];
+        __syncthreads();                                       // rowbuf complete; everybody has read colbuf
+        if (tid == 0) { used[p] = 1; perm[k] = p; kidx[p] = k; }
+        const int kc = k / GJ_TC, kn = k + 1, knc = kn / GJ_TC;
+        const bool colowner = (tc == k % GJ_TC), nextowner = (tc == kn % GJ_TC) && (kn < NT);
+        double rinv[GJ_CT];
+#pragma unroll
+        for (int cc = 0; cc < GJ_CT; ++cc) rinv[cc] = rowbuf[tc + GJ_TC * cc] * inv;
+#pragma unroll
+        for (int a = 0; a < GJ_RT; ++a) {
+            const bool prow = rowowner && (a == ap);
+#pragma unroll
+            for (int cc = 0; cc < GJ_CT; ++cc) {
+                double v = prow ? rinv[cc] : (A[a][cc] - f[a] * rinv[cc]);
+                if (colowner && cc == kc) v = prow ? inv : -f[a] * inv;
+                A[a][cc] = v;
+                if (nextowner && cc == knc) colbuf[tr + GJ_TR * a] = v;      // look-ahead: publish column k+1
+            }
+        }
+        __syncthreads();                                       // colbuf of step k+1 complete; rowbuf free again
+    }
+    if (singular) return false;
+    // ---- write the inverse with both permutations folded in:  Ginv[kidx[i]][perm[j]] = Z[i][j]
+#pragma unroll
+    for (int a = 0; a < GJ_RT; ++a) {
+        const int i = tr + GJ_TR * a;
+#pragma unroll
+        for (int cc = 0; cc < GJ_CT; ++cc) {
+            const int j = tc + GJ_TC * cc;
+            if (i < NT && j < NT) bs.G[(size_t)kidx[i] * NT + perm[j]] = A[a][cc];
+        }
+    }
+    // ---- n x n block: LU with partial pivoting, then the explicit inverse (one column per thread)
     if (!block_lu(bs.Wl, NX, bs.wpiv, s.red)) return false;
+    if (tid < NX) {
+        double col[NX];
+        for (int q = 0; q < NX; ++q) col[q] = (q == tid) ? 1.0 : 0.0;
+        for (int q = 0; q < NX; ++q) { const int pp = bs.wpiv[q]; if (pp != q) { const double t = col[q]; col[q] = col[pp]; col[pp] = t; } }
+        for (int q = 0; q < NX; ++q) {
+            double acc = col[q];
+            for (int e = 0; e < q; ++e) acc -= bs.Wl[q * NX + e] * col[e];
+            col[q] = acc;
+        }
+        for (int q = NX - 1; q >= 0; --q) {
+            double acc = col[q];
+            for (int e = q + 1; e < NX; ++e) acc -= bs.Wl[q * NX + e] * col[e];
+            col[q] = acc / bs.Wl[q * NX + q];
+        }
+        for (int q = 0; q < NX; ++q) bs.Winv[q * NX + tid] = col[q];
+    }
+    __syncthreads();
     return true;
 }
 
-// dy <- (I - cJ)^{-1} dy   (dy holds the right-hand side on entry)
-CPDP_D void bdf_solve(const AuxShared& s, const BdfShared& bs, const double c, double* dy) {
+// dy <- (I - cJ)^{-1} dy   (dy holds the right-hand side on entry; tmp: NYR doubles of scratch)
+CPDP_D void bdf_solve(const AuxShared& s, const BdfShared& bs, const double c, double* dy, double* tmp) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    block_lu_solve(bs.G, NT, bs.piv, dy);
-    double* dW = dy + NT;
-    for (int e = tid; e < NX * NP; e += nt) {
-        const int i = e / NP, k = e % NP;
-        double acc = 0.0;
-        for (int a = 0; a < NX; ++a) acc += dy[i <= a ? tri(i, a) : tri(a, i)] * bs.Cm[a * NP + k];
-        dW[e] += c * acc;
+    __syncthreads();
+    for (int k = tid; k < NT; k += nt) {                       // X = Ginv * B_P
+        const double* g = bs.G + (size_t)k * NT;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int m = 0;
+        for (; m + 3 < NT; m += 4) { a0 += g[m] * dy[m]; a1 += g[m + 1] * dy[m + 1]; a2 += g[m + 2] * dy[m + 2]; a3 += g[m + 3] * dy[m + 3]; }
+        for (; m < NT; ++m) a0 += g[m] * dy[m];
+        tmp[k] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
-    if (tid < NP) {          // one right-hand-side column per thread
-        const int k = tid;
-        for (int q = 0; q < NX; ++q) { const int p = bs.wpiv[q]; if (p != q) { const double t = dW[q * NP + k]; dW[q * NP + k] = dW[p * NP + k]; dW[p * NP + k] = t; } }
-        for (int q = 0; q < NX; ++q) {
-            double acc = dW[q * NP + k];
-            for (int a = 0; a < q; ++a) acc -= bs.Wl[q * NX + a] * dW[a * NP + k];
-            dW[q * NP + k] = acc;
-        }
-        for (int q = NX - 1; q >= 0; --q) {
-            double acc = dW[q * NP + k];
-            for (int a = q + 1; a < NX; ++a) acc -= bs.Wl[q * NX + a] * dW[a * NP + k];
-            dW[q * NP + k] = acc / bs.Wl[q * NX + q];
-        }
+    double* dW = dy + NT;
+    for (int e = tid; e < NX * NP; e += nt) {                  // B_W + c X C
+        const int i = e / NP, k = e % NP;
+        double acc = 0.0;
+        for (int a = 0; a < NX; ++a) acc += tmp[i <= a ? tri(i, a) : tri(a, i)] * bs.Cm[a * NP + k];
+        tmp[NT + e] = dW[e] + c * acc;
+    }
+    for (int k = tid; k < NT; k += nt) dy[k] = tmp[k];
+    __syncthreads();
+    for (int e = tid; e < NX * NP; e += nt) {                  // dW = (I + cL)^{-1} (...)
+        const int i = e / NP, k = e % NP;
+        double acc = 0.0;
+        for (int a = 0; a < NX; ++a) acc += bs.Winv[i * NX + a] * tmp[NT + a * NP + k];
+        dW[e] = acc;
     }
     __syncthreads();
 }
@@ -372,7 +486,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                     }
                     fin = block_reduce(fin, s.red, true);
                     if (fin != 0.0) break;
-                    bdf_solve(s, bs, c_lu, bs.dy);
+                    bdf_solve(s, bs, c_lu, bs.dy, bs.tmp);
                     const double dy_norm = bdf_norm(s, bs.dy, bs.scale, 1.0);
                     const bool have_rate = dy_norm_old >= 0.0;
                     const double rate = have_rate ? dy_norm / dy_norm_old : 0.0;
@@ -448,12 +562,12 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
 
 constexpr int BDF_SMEM_DOUBLES = MSZ + (2 * NX + NU) + (2 * BDF_THREADS + 2) + NX * NX + 2 * NU * NX + NU * NP
                                  + NT * NT + 4 * NX * NX + NX * NP + NX * NU + BDF_NROWS * NYR + 7 * NYR + 36 + 8 + NYR
-                                 + (NT + NX + 4) / 2 + 2;
+                                 + NX * NX + 2 * BDF_GJ_NP + NYR + (3 * BDF_GJ_NP + NX + 4) / 2 + 2;
 
 // k_riccati_bdf: backward sweep of COCSys.auxSysSolver as shipped (CPDP.py:327-338).
 CPDP_GLOBAL void __launch_bounds__(BDF_THREADS) k_riccati_bdf(AuxArgs a) {
     CPDP_DYN_SMEM(smem);
-    CPDP_SHARED int s_ti[NT], s_tj[NT];
+    CPDP_SHARED int s_ti[NT], s_tj[NT], s_tab[SPTAB_INTS];
     CPDP_SHARED double s_hxx[NX * NX], s_hxe[NX * NP];
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     if (a.solve_status && (a.solve_status[b] == ST_NUMERIC || a.solve_status[b] == ST_RUNNING)) {
@@ -476,6 +590,7 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS) k_riccati_bdf(AuxArgs a) {
         s_ti[q] = i; s_tj[q] = i + rem;
     }
     for (int q = tid; q < MSZ; q += nt) s.M[q] = 0.0;
+    aux_tables(s, s_tab);
     BdfShared bs;
     bs.G = carve(ptr, NT * NT); bs.Wl = carve(ptr, NX * NX); bs.Lm = carve(ptr, NX * NX); bs.Am = carve(ptr, NX * NX);
     bs.Rm = carve(ptr, NX * NX); bs.Cm = carve(ptr, NX * NP); bs.GH = carve(ptr, NX * NU);
@@ -485,8 +600,9 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS) k_riccati_bdf(AuxArgs a) {
     bs.RU = carve(ptr, 36);
     double* tms = carve(ptr, 8);
     double* y = carve(ptr, NYR);
-    bs.piv = (int*)carve(ptr, (NT + NX + 4) / 2 + 2);
-    bs.wpiv = bs.piv + NT + 1;
+    bs.Winv = carve(ptr, NX * NX); bs.gjbuf = carve(ptr, 2 * BDF_GJ_NP); bs.tmp = carve(ptr, NYR);
+    bs.piv = (int*)carve(ptr, (3 * BDF_GJ_NP + NX + 4) / 2 + 2);
+    bs.wpiv = bs.piv + 3 * BDF_GJ_NP + 1;
     const int N = a.N;
     AuxProblem p;
     p.X = a.X + (size_t)b * (N + 1) * NX; p.U = a.U + (size_t)b * (N + 1) * NU; p.Lam = a.Lam + (size_t)b * (N + 1) * NX;
