@@ -15,7 +15,7 @@ GEN_DIR = os.path.join(CSRC, "generated")
 LIB_DIR = os.path.join(_PKG, "lib")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
+              "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden"] + os.environ.get("CPDP_EXTRA_NVCC_FLAGS", "").split()
 
 STATUS_NAMES = {0: "running", 1: "converged", 2: "max_iter", 3: "linesearch_fail", 4: "numeric"}
 

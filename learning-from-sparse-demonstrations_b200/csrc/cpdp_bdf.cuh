@@ -28,11 +28,13 @@ constexpr int BDF_THREADS = 128;
 constexpr int BDF_MAX_ORDER = 5;
 constexpr int BDF_NEWTON_MAXITER = 4;
 constexpr int BDF_NROWS = BDF_MAX_ORDER + 3;
-constexpr int BDF_GJ_NP = ((NT + 15) / 16) * 16 > ((NT + 7) / 8) * 8 ? ((NT + 15) / 16) * 16 : ((NT + 7) / 8) * 8;   // = GJ_NP below
 
 struct BdfShared {
-    double* G;      // [NT*NT]  LU of the packed operator X -> X + c (L X + X L')
-    double* Wl;     // [NX*NX]  LU of I + c L
+    double* Tr; double* Ti;   // [NX*NX]  Schur form L = Z T Z^H (T upper triangular)
+    double* Zr; double* Zi;   // [NX*NX]
+    double* Fr; double* Fi;   // [NX*NX]  scratch of the factor / solve steps
+    double* Gr; double* Gi;   // [NX*NX]
+    double* Dr; double* Di;   // [NT]     1 / ((1/2 + c t_ii) + conj(1/2 + c t_jj))
     double* Lm;     // [NX*NX]  L at the Jacobian point
     double* Cm;     // [NX*NP]  C at the Jacobian point
     double* GH;     // [NX*NU]  scratch: fu Huu^{-1}
@@ -42,75 +44,14 @@ struct BdfShared {
     double* ypred; double* scale; double* psi; double* d; double* y; double* f; double* dy;
     double* RU;     // [6*6]
     double* Winv;   // [NX*NX]  inverse of I + c L
-    double* gjbuf;  // [2*GJ_NP] pivot column / pivot row exchange of the Gauss-Jordan steps
     double* tmp;    // [NYR]    scratch of bdf_solve
-    int* piv;       // [3*GJ_NP] used flags, perm, kidx
-    int* wpiv;      // [NX]
+    int* flag;      // [2]
 };
 
 CPDP_HD double bdf_kappa(int k) { const double v[6] = {0.0, -0.1850, -1.0 / 9, -0.0823, -0.0415, 0.0}; return v[k]; }
 CPDP_HD double bdf_gamma(int k) { double g = 0.0; for (int i = 1; i <= k; ++i) g += 1.0 / i; return g; }
 CPDP_HD double bdf_alpha(int k) { return (1.0 - bdf_kappa(k)) * bdf_gamma(k); }
 CPDP_HD double bdf_error_const(int k) { return bdf_kappa(k) * bdf_gamma(k) + 1.0 / (k + 1); }
-
-// (value, index) arg-max over the CTA, ties to the smaller index; same butterfly on GPU and in the emulation.
-CPDP_D int block_argmax(double v, int idx, double* red, double& vmax) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    int* redi = (int*)(red + nt);
-#ifdef __CUDACC__
-    for (int o = 16; o > 0; o >>= 1) {
-        const double x = __shfl_xor_sync(0xffffffffu, v, o);
-        const int xi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (x > v || (x == v && xi < idx)) { v = x; idx = xi; }
-    }
-    __syncthreads();
-    if ((tid & 31) == 0) { red[tid >> 5] = v; redi[tid >> 5] = idx; }
-    __syncthreads();
-    double r = red[0]; int ri = redi[0];
-    for (int i = 1; i < (nt >> 5); ++i) if (red[i] > r || (red[i] == r && redi[i] < ri)) { r = red[i]; ri = redi[i]; }
-#else
-    for (int o = 16; o > 0; o >>= 1) {
-        __syncthreads();
-        red[tid] = v; redi[tid] = idx;
-        __syncthreads();
-        const double x = red[tid ^ o]; const int xi = redi[tid ^ o];
-        if (x > v || (x == v && xi < idx)) { v = x; idx = xi; }
-    }
-    __syncthreads();
-    red[tid] = v; redi[tid] = idx;
-    __syncthreads();
-    double r = red[0]; int ri = redi[0];
-    for (int i = 32; i < nt; i += 32) if (red[i] > r || (red[i] == r && redi[i] < ri)) { r = red[i]; ri = redi[i]; }
-#endif
-    vmax = r;
-    return ri;
-}
-
-// In-place LU with partial pivoting of the row-major n x n matrix A in shared memory by the whole CTA
-// (right-looking, one column per step; rows over warps, columns over lanes).  Returns false if singular.
-CPDP_D bool block_lu(double* A, const int n, int* piv, double* red) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int lane = tid & 31, wrp = tid >> 5, nw = nt >> 5;
-    for (int k = 0; k < n; ++k) {
-        double best = -1.0; int bi = k;
-        for (int i = k + tid; i < n; i += nt) { const double v = fabs(A[i * n + k]); if (v > best) { best = v; bi = i; } }
-        double vmax;
-        const int p = block_argmax(best, bi, red, vmax);
-        if (!(vmax > 0.0)) return false;
-        if (tid == 0) piv[k] = p;
-        if (p != k) for (int j = tid; j < n; j += nt) { const double t = A[k * n + j]; A[k * n + j] = A[p * n + j]; A[p * n + j] = t; }
-        __syncthreads();
-        const double inv = 1.0 / A[k * n + k];
-        for (int i = k + 1 + tid; i < n; i += nt) A[i * n + k] *= inv;
-        __syncthreads();
-        for (int i = k + 1 + wrp; i < n; i += nw) {
-            const double l = A[i * n + k];
-            for (int j = k + 1 + lane; j < n; j += 32) A[i * n + j] -= l * A[k * n + j];
-        }
-        __syncthreads();
-    }
-    return true;
-}
 
 // Closed-form Jacobian data at (PMP matrices M, packed state yJ):  L = A' - P R,  C = R W - r_
 // with A = fx - fu Huu^{-1} Hxu', R = fu Huu^{-1} fu', r_ = fe - fu Huu^{-1} Hue  (CPDP.py:262-270).
@@ -156,150 +97,263 @@ CPDP_D void bdf_jacobian(const AuxShared& s, const BdfShared& bs, const double* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Inverse of the packed Newton operator  X -> X + c (L X + X L')  (NT x NT, NT = n(n+1)/2) held in REGISTERS.
-// The CTA is an 8 x 16 grid of threads (thread t: row group tr = t % 8, column group tc = t / 8); element (i, j)
-// lives in thread (i % 8, j % 16), local slot (i / 8, j / 16).  In-place Gauss-Jordan with implicit partial pivoting:
-// rows are never swapped, the pivot row of step k is only marked as used.  Per step the pivot column and the pivot row
-// travel through shared memory (2 barriers), the rank-1 update runs on register tiles (FP64-pipe bound instead of
-// shared-memory bound).  The result is written to shared memory with both permutations folded in, so that a Newton
-// solve is one plain matrix-vector product.
+// Newton systems through ONE Schur form per Jacobian (Bartels-Stewart).  With L = Z T Z^H (Z unitary, T upper
+// triangular, complex) the packed operator  X -> X + c (L X + X L')  becomes, for Y = Z^H X Z, C = Z^H B Z,
+//     (1/2 + c T) Y + Y (1/2 + c T)^H = C          solved entry by entry along anti-diagonals,
+// and I + c L = Z (I + c T) Z^H.  Nothing has to be re-factorised when the step size (c) changes: scipy's "LU"
+// events only recompute the reciprocals 1 / (1 + c (t_ii + conj t_jj)) and the n x n inverse of I + c L.
+// The Schur form is computed by warp 0: Givens reduction to Hessenberg form, Francis double-shift QR in real
+// arithmetic (2 x 2 blocks left as they come), then one complex Givens rotation per 2 x 2 block.
 // ------------------------------------------------------------------------------------------------
-constexpr int GJ_TR = 8, GJ_TC = 16;
-constexpr int GJ_RT = (NT + GJ_TR - 1) / GJ_TR;        // rows per thread
-constexpr int GJ_CT = (NT + GJ_TC - 1) / GJ_TC;        // columns per thread
-constexpr int GJ_NP = GJ_RT * GJ_TR > GJ_CT * GJ_TC ? GJ_RT * GJ_TR : GJ_CT * GJ_TC;   // padded extent
-static_assert(BDF_THREADS == GJ_TR * GJ_TC, "thread grid of the Gauss-Jordan tiles");
-static_assert(GJ_NP == BDF_GJ_NP, "padded extent");
-
-// coefficient of X_uv (u <= v) in row (i <= j) of  X + c (L X + X L')  for symmetric X
-CPDP_D double gj_entry(const double* Lm, const double c, int i, int j, int u, int v) {
-    double acc = 0.0;
-    if (j == v) acc += Lm[i * NX + u];
-    if (j == u && u != v) acc += Lm[i * NX + v];
-    if (i == u) acc += Lm[j * NX + v];
-    if (i == v && u != v) acc += Lm[j * NX + u];
-    return ((i == u && j == v) ? 1.0 : 0.0) + c * acc;
-}
-
-// arg-max of |col[i]| over rows that are not used yet; every thread returns the same (p, value); ties -> smallest i
-CPDP_D int gj_pivot(const double* col, const int* used, double& pval) {
+static_assert(NX <= 16, "warp-0 sections map one lane per row/column and 16 + lane per row of Z");
 #ifdef __CUDACC__
-    const int lane = threadIdx.x & 31;
-    double best = -1.0; int bi = 0x7fffffff;
-    for (int i = lane; i < NT; i += 32) {
-        const double v = used[i] ? -1.0 : fabs(col[i]);
-        if (v > best) { best = v; bi = i; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        const double x = __shfl_xor_sync(0xffffffffu, best, o);
-        const int xi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (x > best || (x == best && xi < bi)) { best = x; bi = xi; }
-    }
+#define CPDP_W0_SYNC() __syncwarp()
 #else
-    double best = -1.0; int bi = 0x7fffffff;
-    for (int i = 0; i < NT; ++i) {
-        const double v = used[i] ? -1.0 : fabs(col[i]);
-        if (v > best) { best = v; bi = i; }
-    }
+#define CPDP_W0_SYNC() __syncthreads()
 #endif
-    pval = best;
-    return bi;
+
+// Real Schur form by warp 0 (every lane runs the same control flow on the same shared-memory values).
+// H: in L, out quasi-upper-triangular T (exact zeros below the sub-diagonal); Z: out orthogonal, L = Z T Z'.
+CPDP_D bool schur_real_w0(double* H, double* Z) {
+    constexpr int n = NX;
+    const int lane = threadIdx.x;
+    const double EPS = 2.220446049250313e-16;
+#define h_(i, j) H[(i) * n + (j)]
+    if (lane < 32) for (int i = lane; i < n * n; i += 32) Z[i] = (i / n == i % n) ? 1.0 : 0.0;
+    CPDP_W0_SYNC();
+    // ---- Hessenberg form by Givens rotations in the planes (i-1, i)
+    for (int j = 0; j < n - 2; ++j)
+        for (int i = n - 1; i >= j + 2; --i) {
+            const double a = h_(i - 1, j), b = h_(i, j);
+            if (b == 0.0) continue;
+            const double sc = fabs(a) + fabs(b);
+            const double rr = sc * sqrt((a / sc) * (a / sc) + (b / sc) * (b / sc));
+            const double c = a / rr, s = b / rr;
+            CPDP_W0_SYNC();
+            if (lane >= j && lane < n) {
+                const double t1 = h_(i - 1, lane), t2 = h_(i, lane);
+                h_(i - 1, lane) = c * t1 + s * t2;
+                h_(i, lane) = (lane == j) ? 0.0 : c * t2 - s * t1;
+            }
+            CPDP_W0_SYNC();
+            if (lane < n) {
+                const double t1 = h_(lane, i - 1), t2 = h_(lane, i);
+                h_(lane, i - 1) = c * t1 + s * t2;
+                h_(lane, i) = c * t2 - s * t1;
+            } else if (lane >= 16 && lane < 16 + n) {
+                const int k = lane - 16;
+                const double t1 = Z[k * n + i - 1], t2 = Z[k * n + i];
+                Z[k * n + i - 1] = c * t1 + s * t2;
+                Z[k * n + i] = c * t2 - s * t1;
+            }
+            CPDP_W0_SYNC();
+        }
+    double norm = 0.0;
+    for (int i = 0; i < n; ++i) for (int j = (i > 0 ? i - 1 : 0); j < n; ++j) norm += fabs(h_(i, j));
+    // ---- Francis double-shift QR sweeps, full Schur form (rows/columns updated over the whole matrix)
+    int en = n - 1;
+    while (en >= 0) {
+        int its = 0;
+        while (true) {
+            int l;
+            for (l = en; l >= 1; --l) {
+                double s = fabs(h_(l - 1, l - 1)) + fabs(h_(l, l));
+                if (s == 0.0) s = norm;
+                if (fabs(h_(l, l - 1)) <= EPS * s) break;
+            }
+            if (l >= 1) {
+                CPDP_W0_SYNC();
+                if (lane == 0) h_(l, l - 1) = 0.0;
+                CPDP_W0_SYNC();
+            }
+            if (l == en) { en -= 1; break; }
+            if (l == en - 1) { en -= 2; break; }
+            if (its >= 600) return false;
+            double x = h_(en, en), y = h_(en - 1, en - 1), w = h_(en, en - 1) * h_(en - 1, en);
+            // exceptional shift every 14th sweep: blocks holding two nearly identical complex pairs (the x/y symmetry
+            // of the quadrotor) converge only linearly under the standard shifts and can need > 100 sweeps
+            if (its > 0 && its % 14 == 0) {
+                const double s = fabs(h_(en, en - 1)) + fabs(h_(en - 1, en - 2));
+                x = y = 0.75 * s + h_(en, en);
+                w = -0.4375 * s * s;
+            }
+            ++its;
+            int m;
+            double p = 0.0, q = 0.0, r = 0.0;
+            for (m = en - 2; m >= l; --m) {
+                const double z = h_(m, m), r0 = x - z, s0 = y - z;
+                p = (r0 * s0 - w) / h_(m + 1, m) + h_(m, m + 1);
+                q = h_(m + 1, m + 1) - z - r0 - s0;
+                r = h_(m + 2, m + 1);
+                const double s = fabs(p) + fabs(q) + fabs(r);
+                if (s != 0.0) { p /= s; q /= s; r /= s; }
+                if (m == l) break;
+                const double u = fabs(h_(m, m - 1)) * (fabs(q) + fabs(r));
+                const double v = fabs(p) * (fabs(h_(m - 1, m - 1)) + fabs(z) + fabs(h_(m + 1, m + 1)));
+                if (u <= EPS * v) break;
+            }
+            for (int k = m; k <= en - 1; ++k) {
+                const bool notlast = (k != en - 1);
+                double x2 = 0.0;
+                if (k != m) {
+                    p = h_(k, k - 1); q = h_(k + 1, k - 1); r = notlast ? h_(k + 2, k - 1) : 0.0;
+                    x2 = fabs(p) + fabs(q) + fabs(r);
+                    if (x2 == 0.0) continue;
+                    p /= x2; q /= x2; r /= x2;
+                }
+                double s = sqrt(p * p + q * q + r * r);
+                if (s == 0.0) continue;
+                if (p < 0.0) s = -s;
+                CPDP_W0_SYNC();
+                if (lane == 0) {
+                    if (k != m) { h_(k, k - 1) = -s * x2; h_(k + 1, k - 1) = 0.0; if (notlast) h_(k + 2, k - 1) = 0.0; }
+                    else if (l != m) h_(k, k - 1) = -h_(k, k - 1);
+                }
+                p += s;
+                const double xx = p / s, yy = q / s, zz = r / s;
+                q /= p; r /= p;
+                if (lane >= k && lane < n) {
+                    double pp = h_(k, lane) + q * h_(k + 1, lane);
+                    if (notlast) { pp += r * h_(k + 2, lane); h_(k + 2, lane) -= pp * zz; }
+                    h_(k, lane) -= pp * xx;
+                    h_(k + 1, lane) -= pp * yy;
+                }
+                CPDP_W0_SYNC();
+                const int imax = (en < k + 3) ? en : k + 3;
+                if (lane <= imax) {
+                    double pp = xx * h_(lane, k) + yy * h_(lane, k + 1);
+                    if (notlast) { pp += zz * h_(lane, k + 2); h_(lane, k + 2) -= pp * r; }
+                    h_(lane, k) -= pp;
+                    h_(lane, k + 1) -= pp * q;
+                } else if (lane >= 16 && lane < 16 + n) {
+                    const int i = lane - 16;
+                    double pp = xx * Z[i * n + k] + yy * Z[i * n + k + 1];
+                    if (notlast) { pp += zz * Z[i * n + k + 2]; Z[i * n + k + 2] -= pp * r; }
+                    Z[i * n + k] -= pp;
+                    Z[i * n + k + 1] -= pp * q;
+                }
+                CPDP_W0_SYNC();
+            }
+        }
+    }
+#undef h_
+    return true;
 }
 
-// Assemble and invert I - cJ in its structured form: bs.G <- inverse of the packed operator (row-major NT x NT),
-// bs.Wl <- inverse of I + c L.
-CPDP_D bool bdf_factor(const AuxShared& s, const BdfShared& bs, const double c) {
+// Complex Schur form L = Z T Z^H from bs.Lm, by warp 0; result in (Tr,Ti), (Zr,Zi).  Returns false (uniformly over
+// the CTA) if the QR iteration did not converge.
+CPDP_D bool bdf_schur(const BdfShared& bs) {
+    constexpr int n = NX;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int tr = tid % GJ_TR, tc = tid / GJ_TR;
-    double* colbuf = bs.gjbuf;                  // [GJ_NP] pivot column of the current step
-    double* rowbuf = bs.gjbuf + GJ_NP;          // [GJ_NP] pivot row of the current step
-    int* used = bs.piv;                         // [GJ_NP] row already used as a pivot
-    int* perm = bs.piv + GJ_NP;                 // [NT]    perm[k] = pivot row of step k
-    int* kidx = bs.piv + 2 * GJ_NP;             // [GJ_NP] kidx[i] = step at which row i was the pivot
-    double A[GJ_RT][GJ_CT];
     __syncthreads();
-    // ---- assemble the register tiles; publish column 0
-#pragma unroll
-    for (int a = 0; a < GJ_RT; ++a) {
-        const int q = tr + GJ_TR * a;
-#pragma unroll
-        for (int cc = 0; cc < GJ_CT; ++cc) {
-            const int col = tc + GJ_TC * cc;
-            double v = 0.0;
-            if (q < NT && col < NT) v = gj_entry(bs.Lm, c, s.ti[q], s.tj[q], s.ti[col], s.tj[col]);
-            A[a][cc] = v;
-            if (col == 0) colbuf[q] = v;
-        }
-    }
-    for (int i = tid; i < GJ_NP; i += nt) { used[i] = (i >= NT) ? 1 : 0; rowbuf[i] = 0.0; }
-    for (int i = tid; i < NX * NX; i += nt) bs.Wl[i] = ((i / NX == i % NX) ? 1.0 : 0.0) + c * bs.Lm[i];
+    for (int i = tid; i < n * n; i += nt) { bs.Tr[i] = bs.Lm[i]; bs.Ti[i] = 0.0; bs.Zi[i] = 0.0; }
+    if (tid == 0) bs.flag[0] = 1;
     __syncthreads();
-    bool singular = false;
-    for (int k = 0; k < NT; ++k) {
-        double pval;
-        const int p = gj_pivot(colbuf, used, pval);           // every thread computes the same pivot
-        if (!(pval > 0.0)) { singular = true; break; }
-        const int ap = p / GJ_TR;
-        const bool rowowner = (tr == p % GJ_TR);
-        if (rowowner) {
-#pragma unroll
-            for (int a = 0; a < GJ_RT; ++a) if (a == ap) {
-#pragma unroll
-                for (int cc = 0; cc < GJ_CT; ++cc) rowbuf[tc + GJ_TC * cc] = A[a][cc];
+#ifdef __CUDACC__
+    if (tid < 32)
+#endif
+    {
+        const int lane = tid;
+        const bool ok = schur_real_w0(bs.Tr, bs.Zr);
+        CPDP_W0_SYNC();
+        if (!ok && lane == 0) bs.flag[0] = 0;
+        // ---- one unitary rotation per 2 x 2 block:  G = [[c, s], [-conj(s), c]],  T <- G T G^H,  Z <- Z G^H
+        for (int j = 0; ok && j < n - 1; ++j) {
+            const double cc = bs.Tr[(j + 1) * n + j];
+            if (cc == 0.0) continue;
+            const double a = bs.Tr[j * n + j], b = bs.Tr[j * n + j + 1], d = bs.Tr[(j + 1) * n + j + 1];
+            const double hd = 0.5 * (a - d), disc = hd * hd + b * cc;
+            double v1r, v1i;                                           // eigenvector [lambda - d, cc]
+            if (disc >= 0.0) { v1r = hd + (hd >= 0.0 ? sqrt(disc) : -sqrt(disc)); v1i = 0.0; }
+            else { v1r = hd; v1i = sqrt(-disc); }
+            const double av1 = sqrt(v1r * v1r + v1i * v1i);
+            const double rho = sqrt(av1 * av1 + cc * cc);
+            double cr, sr, si;
+            if (av1 == 0.0) { cr = 0.0; sr = (cc >= 0.0) ? 1.0 : -1.0; si = 0.0; }
+            else { cr = av1 / rho; sr = v1r * cc / (av1 * rho); si = v1i * cc / (av1 * rho); }
+            CPDP_W0_SYNC();
+            if (lane >= j && lane < n) {                               // rows j, j+1
+                const int k = lane;
+                const double xr = bs.Tr[j * n + k], xi = bs.Ti[j * n + k], yr = bs.Tr[(j + 1) * n + k], yi = bs.Ti[(j + 1) * n + k];
+                bs.Tr[j * n + k] = cr * xr + (sr * yr - si * yi);
+                bs.Ti[j * n + k] = cr * xi + (sr * yi + si * yr);
+                bs.Tr[(j + 1) * n + k] = cr * yr - (sr * xr + si * xi);
+                bs.Ti[(j + 1) * n + k] = cr * yi - (sr * xi - si * xr);
             }
-        }
-        double f[GJ_RT];
-#pragma unroll
-        for (int a = 0; a < GJ_RT; ++a) f[a] = colbuf[tr + GJ_TR * a];
-        const double inv = 1.0 / colbuf[p];
-        __syncthreads();                                       // rowbuf complete; everybody has read colbuf
-        if (tid == 0) { used[p] = 1; perm[k] = p; kidx[p] = k; }
-        const int kc = k / GJ_TC, kn = k + 1, knc = kn / GJ_TC;
-        const bool colowner = (tc == k % GJ_TC), nextowner = (tc == kn % GJ_TC) && (kn < NT);
-        double rinv[GJ_CT];
-#pragma unroll
-        for (int cc = 0; cc < GJ_CT; ++cc) rinv[cc] = rowbuf[tc + GJ_TC * cc] * inv;
-#pragma unroll
-        for (int a = 0; a < GJ_RT; ++a) {
-            const bool prow = rowowner && (a == ap);
-#pragma unroll
-            for (int cc = 0; cc < GJ_CT; ++cc) {
-                double v = prow ? rinv[cc] : (A[a][cc] - f[a] * rinv[cc]);
-                if (colowner && cc == kc) v = prow ? inv : -f[a] * inv;
-                A[a][cc] = v;
-                if (nextowner && cc == knc) colbuf[tr + GJ_TR * a] = v;      // look-ahead: publish column k+1
+            CPDP_W0_SYNC();
+            if (lane <= j + 1) {                                       // columns j, j+1 of T
+                const int k = lane;
+                const double xr = bs.Tr[k * n + j], xi = bs.Ti[k * n + j], yr = bs.Tr[k * n + j + 1], yi = bs.Ti[k * n + j + 1];
+                bs.Tr[k * n + j] = cr * xr + (sr * yr + si * yi);
+                bs.Ti[k * n + j] = cr * xi + (sr * yi - si * yr);
+                bs.Tr[k * n + j + 1] = cr * yr - (sr * xr - si * xi);
+                bs.Ti[k * n + j + 1] = cr * yi - (sr * xi + si * xr);
+            } else if (lane >= 16 && lane < 16 + n) {                  // columns j, j+1 of Z
+                const int k = lane - 16;
+                const double xr = bs.Zr[k * n + j], xi = bs.Zi[k * n + j], yr = bs.Zr[k * n + j + 1], yi = bs.Zi[k * n + j + 1];
+                bs.Zr[k * n + j] = cr * xr + (sr * yr + si * yi);
+                bs.Zi[k * n + j] = cr * xi + (sr * yi - si * yr);
+                bs.Zr[k * n + j + 1] = cr * yr - (sr * xr - si * xi);
+                bs.Zi[k * n + j + 1] = cr * yi - (sr * xi + si * xr);
             }
-        }
-        __syncthreads();                                       // colbuf of step k+1 complete; rowbuf free again
-    }
-    if (singular) return false;
-    // ---- write the inverse with both permutations folded in:  Ginv[kidx[i]][perm[j]] = Z[i][j]
-#pragma unroll
-    for (int a = 0; a < GJ_RT; ++a) {
-        const int i = tr + GJ_TR * a;
-#pragma unroll
-        for (int cc = 0; cc < GJ_CT; ++cc) {
-            const int j = tc + GJ_TC * cc;
-            if (i < NT && j < NT) bs.G[(size_t)kidx[i] * NT + perm[j]] = A[a][cc];
+            CPDP_W0_SYNC();
+            if (lane == 0) { bs.Tr[(j + 1) * n + j] = 0.0; bs.Ti[(j + 1) * n + j] = 0.0; }
+            CPDP_W0_SYNC();
         }
     }
-    // ---- n x n block: LU with partial pivoting, then the explicit inverse (one column per thread)
-    if (!block_lu(bs.Wl, NX, bs.wpiv, s.red)) return false;
-    if (tid < NX) {
-        double col[NX];
-        for (int q = 0; q < NX; ++q) col[q] = (q == tid) ? 1.0 : 0.0;
-        for (int q = 0; q < NX; ++q) { const int pp = bs.wpiv[q]; if (pp != q) { const double t = col[q]; col[q] = col[pp]; col[pp] = t; } }
-        for (int q = 0; q < NX; ++q) {
-            double acc = col[q];
-            for (int e = 0; e < q; ++e) acc -= bs.Wl[q * NX + e] * col[e];
-            col[q] = acc;
+    __syncthreads();
+    return bs.flag[0] != 0;
+}
+
+// scipy's "LU" event for a new c: reciprocals of the Lyapunov pivots and Winv = (I + c L)^{-1} = Re(Z (I + c T)^{-1} Z^H).
+CPDP_D bool bdf_factor(const AuxShared& s, const BdfShared& bs, const double c) {
+    constexpr int n = NX;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __syncthreads();
+    double bad = 0.0;
+    if (tid < n) {                                   // column tid of S = (I + c T)^{-1}  (upper triangular) -> (Fr, Fi)
+        const int j = tid;
+        for (int i = j; i >= 0; --i) {
+            double nr = (i == j) ? 1.0 : 0.0, ni = 0.0;
+            for (int k = i + 1; k <= j; ++k) {
+                const double tr = c * bs.Tr[i * n + k], ti = c * bs.Ti[i * n + k];
+                const double sr = bs.Fr[k * n + j], si = bs.Fi[k * n + j];
+                nr -= tr * sr - ti * si;
+                ni -= tr * si + ti * sr;
+            }
+            const double dr = 1.0 + c * bs.Tr[i * n + i], di = c * bs.Ti[i * n + i];
+            const double dd = dr * dr + di * di;
+            if (!(dd > 0.0)) bad = 1.0;
+            bs.Fr[i * n + j] = (nr * dr + ni * di) / dd;
+            bs.Fi[i * n + j] = (ni * dr - nr * di) / dd;
         }
-        for (int q = NX - 1; q >= 0; --q) {
-            double acc = col[q];
-            for (int e = q + 1; e < NX; ++e) acc -= bs.Wl[q * NX + e] * col[e];
-            col[q] = acc / bs.Wl[q * NX + q];
+        for (int i = j + 1; i < n; ++i) { bs.Fr[i * n + j] = 0.0; bs.Fi[i * n + j] = 0.0; }
+    }
+    for (int q = tid; q < NT; q += nt) {             // 1 / ((1/2 + c t_ii) + conj(1/2 + c t_jj))
+        const int i = s.ti[q], j = s.tj[q];
+        const double dr = 1.0 + c * (bs.Tr[i * n + i] + bs.Tr[j * n + j]), di = c * (bs.Ti[i * n + i] - bs.Ti[j * n + j]);
+        const double dd = dr * dr + di * di;
+        if (!(dd > 0.0)) bad = 1.0;
+        bs.Dr[q] = dr / dd; bs.Di[q] = -di / dd;
+    }
+    bad = block_reduce(bad, s.red, true);
+    if (bad != 0.0) return false;
+    for (int e = tid; e < n * n; e += nt) {          // G = Z S
+        const int i = e / n, k = e % n;
+        double gr = 0.0, gi = 0.0;
+        for (int j = 0; j <= k; ++j) {
+            const double zr = bs.Zr[i * n + j], zi = bs.Zi[i * n + j], sr = bs.Fr[j * n + k], si = bs.Fi[j * n + k];
+            gr += zr * sr - zi * si;
+            gi += zr * si + zi * sr;
         }
-        for (int q = 0; q < NX; ++q) bs.Winv[q * NX + tid] = col[q];
+        bs.Gr[e] = gr; bs.Gi[e] = gi;
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += nt) {          // Winv = Re(G Z^H)
+        const int i = e / n, l = e % n;
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc += bs.Gr[i * n + k] * bs.Zr[l * n + k] + bs.Gi[i * n + k] * bs.Zi[l * n + k];
+        bs.Winv[e] = acc;
     }
     __syncthreads();
     return true;
@@ -307,15 +361,93 @@ CPDP_D bool bdf_factor(const AuxShared& s, const BdfShared& bs, const double c) 
 
 // dy <- (I - cJ)^{-1} dy   (dy holds the right-hand side on entry; tmp: NYR doubles of scratch)
 CPDP_D void bdf_solve(const AuxShared& s, const BdfShared& bs, const double c, double* dy, double* tmp) {
+    constexpr int n = NX;
     const int tid = threadIdx.x, nt = blockDim.x;
     __syncthreads();
-    for (int k = tid; k < NT; k += nt) {                       // X = Ginv * B_P
-        const double* g = bs.G + (size_t)k * NT;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int m = 0;
-        for (; m + 3 < NT; m += 4) { a0 += g[m] * dy[m]; a1 += g[m + 1] * dy[m + 1]; a2 += g[m + 2] * dy[m + 2]; a3 += g[m + 3] * dy[m + 3]; }
-        for (; m < NT; ++m) a0 += g[m] * dy[m];
-        tmp[k] = (a0 + a1) + (a2 + a3);
+    for (int e = tid; e < n * n; e += nt) {          // F = B Z, B = sym(dy[0:NT])
+        const int i = e / n, k = e % n;
+        double fr = 0.0, fi = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const double b = dy[i <= j ? tri(i, j) : tri(j, i)];
+            fr += b * bs.Zr[j * n + k]; fi += b * bs.Zi[j * n + k];
+        }
+        bs.Fr[e] = fr; bs.Fi[e] = fi;
+    }
+    __syncthreads();
+    for (int q = tid; q < NT; q += nt) {             // C = Z^H F (upper triangle) -> (Gr, Gi)
+        const int i = s.ti[q], j = s.tj[q];
+        double cr = 0.0, ci = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double zr = bs.Zr[k * n + i], zi = bs.Zi[k * n + i], fr = bs.Fr[k * n + j], fi = bs.Fi[k * n + j];
+            cr += zr * fr + zi * fi;
+            ci += zr * fi - zi * fr;
+        }
+        bs.Gr[i * n + j] = cr; bs.Gi[i * n + j] = ci;
+    }
+    __syncthreads();
+    // ---- (1/2 + cT) Y + Y (1/2 + cT)^H = C along anti-diagonals i + j = d (warp 0; 4 lanes per entry); Y overwrites C,
+    //      both triangles are kept (Y is Hermitian)
+#ifdef __CUDACC__
+    if (tid < 32)
+#endif
+    {
+        const int e = tid >> 2, sub = tid & 3;
+        for (int d = 2 * (n - 1); d >= 0; --d) {
+            const int ilo = (d > n - 1) ? d - (n - 1) : 0;
+            const int i = ilo + e, j = d - i;
+            const bool valid = (tid < 32) && (i <= j);
+            double ar = 0.0, ai = 0.0;
+            if (valid) {
+                for (int k = i + 1 + sub; k < n; k += 4) {           // T_ik Y_kj
+                    const double tr = bs.Tr[i * n + k], ti = bs.Ti[i * n + k], yr = bs.Gr[k * n + j], yi = bs.Gi[k * n + j];
+                    ar += tr * yr - ti * yi;
+                    ai += tr * yi + ti * yr;
+                }
+                for (int k = j + 1 + sub; k < n; k += 4) {           // Y_ik conj(T_jk)
+                    const double tr = bs.Tr[j * n + k], ti = bs.Ti[j * n + k], yr = bs.Gr[i * n + k], yi = bs.Gi[i * n + k];
+                    ar += yr * tr + yi * ti;
+                    ai += yi * tr - yr * ti;
+                }
+            }
+#ifdef __CUDACC__
+            ar += __shfl_xor_sync(0xffffffffu, ar, 1); ai += __shfl_xor_sync(0xffffffffu, ai, 1);
+            ar += __shfl_xor_sync(0xffffffffu, ar, 2); ai += __shfl_xor_sync(0xffffffffu, ai, 2);
+#else
+            __syncthreads();
+            if (tid < 32) { s.red[tid] = ar; s.red[32 + tid] = ai; }
+            __syncthreads();
+            if (tid < 32 && sub == 0) {
+                ar = (s.red[tid] + s.red[tid + 1]) + (s.red[tid + 2] + s.red[tid + 3]);
+                ai = (s.red[32 + tid] + s.red[32 + tid + 1]) + (s.red[32 + tid + 2] + s.red[32 + tid + 3]);
+            }
+#endif
+            if (valid && sub == 0) {
+                const double rr = bs.Gr[i * n + j] - c * ar, ri = bs.Gi[i * n + j] - c * ai;
+                const int q = tri(i, j);
+                const double yr = rr * bs.Dr[q] - ri * bs.Di[q], yi = rr * bs.Di[q] + ri * bs.Dr[q];
+                bs.Gr[i * n + j] = yr; bs.Gi[i * n + j] = (i == j) ? 0.0 : yi;
+                if (i != j) { bs.Gr[j * n + i] = yr; bs.Gi[j * n + i] = -yi; }
+            }
+            CPDP_W0_SYNC();
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += nt) {          // F = Z Y
+        const int i = e / n, k = e % n;
+        double fr = 0.0, fi = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const double zr = bs.Zr[i * n + j], zi = bs.Zi[i * n + j], yr = bs.Gr[j * n + k], yi = bs.Gi[j * n + k];
+            fr += zr * yr - zi * yi;
+            fi += zr * yi + zi * yr;
+        }
+        bs.Fr[e] = fr; bs.Fi[e] = fi;
+    }
+    __syncthreads();
+    for (int q = tid; q < NT; q += nt) {             // X = Re(F Z^H), upper triangle
+        const int i = s.ti[q], l = s.tj[q];
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc += bs.Fr[i * n + k] * bs.Zr[l * n + k] + bs.Fi[i * n + k] * bs.Zi[l * n + k];
+        tmp[q] = acc;
     }
     __syncthreads();
     double* dW = dy + NT;
@@ -392,6 +524,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
     if (!aux_prepare<false>(s, p, tms, 1)) return 2;
     riccati_rhs(s, M0, y, bs.f); ++cnt[0];
     bdf_jacobian(s, bs, M0, y); ++cnt[3];
+    if (!bdf_schur(bs)) return 4;
     double h_abs;
     {
         const double interval_length = fabs(t1 - t0);
@@ -500,6 +633,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                 if (!converged) {
                     if (current_jac) break;
                     bdf_jacobian(s, bs, M0, bs.ypred); ++cnt[3];
+                    if (!bdf_schur(bs)) return 4;
                     lu_valid = false;
                     current_jac = true;
                 }
@@ -561,8 +695,8 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
 }
 
 constexpr int BDF_SMEM_DOUBLES = MSZ + (2 * NX + NU) + (2 * BDF_THREADS + 2) + NX * NX + 2 * NU * NX + NU * NP
-                                 + NT * NT + 4 * NX * NX + NX * NP + NX * NU + BDF_NROWS * NYR + 7 * NYR + 36 + 8 + NYR
-                                 + NX * NX + 2 * BDF_GJ_NP + NYR + (3 * BDF_GJ_NP + NX + 4) / 2 + 2;
+                                 + 8 * NX * NX + 2 * NT + 4 * NX * NX + NX * NP + NX * NU + BDF_NROWS * NYR + 7 * NYR + 36 + 8 + NYR
+                                 + NYR + 2;
 
 // k_riccati_bdf: backward sweep of COCSys.auxSysSolver as shipped (CPDP.py:327-338).
 CPDP_GLOBAL void __launch_bounds__(BDF_THREADS) k_riccati_bdf(AuxArgs a) {
@@ -592,7 +726,10 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS) k_riccati_bdf(AuxArgs a) {
     for (int q = tid; q < MSZ; q += nt) s.M[q] = 0.0;
     aux_tables(s, s_tab);
     BdfShared bs;
-    bs.G = carve(ptr, NT * NT); bs.Wl = carve(ptr, NX * NX); bs.Lm = carve(ptr, NX * NX); bs.Am = carve(ptr, NX * NX);
+    bs.Tr = carve(ptr, NX * NX); bs.Ti = carve(ptr, NX * NX); bs.Zr = carve(ptr, NX * NX); bs.Zi = carve(ptr, NX * NX);
+    bs.Fr = carve(ptr, NX * NX); bs.Fi = carve(ptr, NX * NX); bs.Gr = carve(ptr, NX * NX); bs.Gi = carve(ptr, NX * NX);
+    bs.Dr = carve(ptr, NT); bs.Di = carve(ptr, NT);
+    bs.Lm = carve(ptr, NX * NX); bs.Am = carve(ptr, NX * NX);
     bs.Rm = carve(ptr, NX * NX); bs.Cm = carve(ptr, NX * NP); bs.GH = carve(ptr, NX * NU);
     bs.D = carve(ptr, BDF_NROWS * NYR);
     bs.ypred = carve(ptr, NYR); bs.scale = carve(ptr, NYR); bs.psi = carve(ptr, NYR); bs.d = carve(ptr, NYR);
@@ -600,9 +737,8 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS) k_riccati_bdf(AuxArgs a) {
     bs.RU = carve(ptr, 36);
     double* tms = carve(ptr, 8);
     double* y = carve(ptr, NYR);
-    bs.Winv = carve(ptr, NX * NX); bs.gjbuf = carve(ptr, 2 * BDF_GJ_NP); bs.tmp = carve(ptr, NYR);
-    bs.piv = (int*)carve(ptr, (3 * BDF_GJ_NP + NX + 4) / 2 + 2);
-    bs.wpiv = bs.piv + 3 * BDF_GJ_NP + 1;
+    bs.Winv = carve(ptr, NX * NX); bs.tmp = carve(ptr, NYR);
+    bs.flag = (int*)carve(ptr, 2);
     const int N = a.N;
     AuxProblem p;
     p.X = a.X + (size_t)b * (N + 1) * NX; p.U = a.U + (size_t)b * (N + 1) * NU; p.Lam = a.Lam + (size_t)b * (N + 1) * NX;
@@ -629,6 +765,16 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS) k_riccati_bdf(AuxArgs a) {
         for (int q = tid; q < NYR; q += nt) PW[(size_t)(k - 1) * NYR + q] = y[q];
         __syncthreads();
     }
+#ifdef CPDP_DEBUG_DUMP
+    if (st == 4) {
+        double* dst = a.Xa + (size_t)b * (N + 1) * NYF;
+        for (int i = tid; i < NX * NX; i += nt) {
+            dst[i] = bs.Lm[i]; dst[NX * NX + i] = bs.Tr[i]; dst[2 * NX * NX + i] = bs.Ti[i];
+            dst[3 * NX * NX + i] = bs.Zr[i]; dst[4 * NX * NX + i] = bs.Zi[i];
+        }
+        if (tid == 0) dst[5 * NX * NX] = (double)bs.flag[0];
+    }
+#endif
     if (tid == 0) {
         a.aux_status[b] = st;
         a.counters[b * NCOUNTERS + 0] = cnt[0]; a.counters[b * NCOUNTERS + 1] = cnt[1];

@@ -31,7 +31,8 @@ static int cpdp_take_error() {
 
 template <class K>
 static void cpdp_prepare_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) {
+    // always opt in: static + dynamic shared memory may exceed 48 KB even when the dynamic part alone does not
+    if (bytes > 32 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess && !g_last_error) g_last_error = (int)e;
     }
