@@ -319,7 +319,7 @@ class Oracle:
         invHuu = np.linalg.inv(Huu)
         return fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu
 
-    def riccati_rhs(self, x, u, lam, th, P, W):
+    def riccati_rhs(self, x, u, lam, th, P, W, reassoc=False):
         """CPDP.py:262-274"""
         fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu = self._coeffs(x, u, lam, th)
         G = fu @ invHuu
@@ -329,9 +329,30 @@ class Oracle:
         Q = Hxx - HxuinvHuu @ Hxu.T
         r = fe - G @ Hue
         q = Hxe - HxuinvHuu @ Hue
+        if reassoc:      # same mathematics, different floating-point association (see ``aux``)
+            P_dot = -(Q + (A.T @ P + P @ A) - P @ (R @ P))
+            W_dot = P @ (R @ W) - (A.T @ W + P @ r) - q
+            return P_dot, W_dot
         P_dot = -(Q + A.T @ P + P @ A - P @ R @ P)
         W_dot = P @ R @ W - A.T @ W - P @ r - q
         return P_dot, W_dot
+
+    def riccati_jac(self, x, u, lam, th, P, W):
+        """Closed-form Jacobian of ``riccati_rhs`` w.r.t. the row-major state [vec P | vec W] (the matrix scipy's BDF
+        approximates by finite differences when the reference calls it without ``jac``, CPDP.py:335):
+        d(Pdot)[dP] = -((A'-PR) dP + dP (A-RP)),  d(Wdot)[dP, dW] = dP (RW - r_) + (PR - A') dW."""
+        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu = self._coeffs(x, u, lam, th)
+        n, r = P.shape[0], W.shape[1]
+        G = fu @ invHuu
+        A = fx - G @ Hxu.T
+        R = G @ fu.T
+        r_ = fe - G @ Hue
+        In = np.eye(n)
+        J = np.zeros((n * n + n * r, n * n + n * r))
+        J[:n * n, :n * n] = -(np.kron(A.T - P @ R, In) + np.kron(In, (A - R @ P).T))
+        J[n * n:, :n * n] = np.kron(In, (R @ W - r_).T)
+        J[n * n:, n * n:] = np.kron(P @ R - A.T, np.eye(r))
+        return J
 
     def aux_controller(self, x, u, lam, th, P, W, Xa):
         """CPDP.py:294-295"""
@@ -346,8 +367,13 @@ class Oracle:
 
     def aux(self, time_grid, X, U, Lam, theta, back=None, fwd=None, return_counts=False):
         """CPDP.py:301-381.  ``back`` / ``fwd`` are the keyword dictionaries handed to solve_ivp for the
-        backward Riccati sweep and the forward sweep; the as-shipped reference is back={'method':'BDF'}, fwd={}."""
-        back = {'method': 'BDF'} if back is None else back
+        backward Riccati sweep and the forward sweep; the as-shipped reference is back={'method':'BDF'}, fwd={}.
+        Two oracle-only keys of ``back``: ``jac='closed'`` hands scipy's BDF the closed-form Jacobian instead of its
+        finite-difference one (same solver, same control logic); ``reassoc=True`` evaluates the Riccati right-hand
+        side with a different association of the same matrix products (measures how far roundoff alone moves the
+        as-shipped result through the finite-difference Jacobian)."""
+        back = dict({'method': 'BDF'} if back is None else back)
+        reassoc = back.pop('reassoc', False)
         fwd = {} if fwd is None else fwd
         n, m, r, N = self.n, self.m, self.r, self.N
         th = np.asarray(theta, dtype=float)
@@ -363,8 +389,14 @@ class Oracle:
             P = vec_PW[:n * n].reshape(n, n)
             W = vec_PW[n * n:].reshape(n, -1)
             x, u, lam = split(t)
-            Pd, Wd = self.riccati_rhs(x, u, lam, th, P, W)
+            Pd, Wd = self.riccati_rhs(x, u, lam, th, P, W, reassoc=reassoc)
             return np.concatenate((Pd.flatten(), Wd.flatten()))
+
+        if back.get('jac') == 'closed':
+            def vec_PW_jac(t, vec_PW):
+                x, u, lam = split(t)
+                return self.riccati_jac(x, u, lam, th, vec_PW[:n * n].reshape(n, n), vec_PW[n * n:].reshape(n, -1))
+            back['jac'] = vec_PW_jac
 
         xT = opt_sol(float(time_grid[-1]))[:n]
         _, _, hxx, hxe = self.fn.term(xT, th, self.pd)

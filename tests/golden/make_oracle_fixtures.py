@@ -4,6 +4,9 @@ Output: tests/golden/oracle_<case>.npz with the converged trajectory and the los
   asshipped : BDF backward (scipy defaults) + RK45 forward (defaults)   = what the reference's COCSys computes
   rk45      : RK45 backward (defaults) + RK45 forward (defaults)
   tight     : rtol 1e-10 / atol 1e-12 both sweeps
+  asshipped_cj : as shipped, but scipy's BDF is handed the closed-form Jacobian instead of its finite-difference one
+  asshipped_ra : as shipped (finite-difference Jacobian), Riccati RHS evaluated with a different association of the
+                 same products -> |dl_asshipped_ra - dl_asshipped| is the reference's own roundoff reproducibility band
 """
 import os
 import sys
@@ -30,7 +33,9 @@ def run_problem(args):
         orc.pd = np.asarray(pd, dtype=float)
     tg, X, U, Lam, info = orc.solve(x0, T, theta, return_info=True)
     out = dict(X=X, U=U, Lam=Lam, iters=info['iters'], J=info['J'], kkt=info['kkt'])
-    for tag, back, fwd in (('asshipped', {'method': 'BDF'}, {}), ('rk45', {}, {}), ('tight', TIGHT, TIGHT)):
+    for tag, back, fwd in (('asshipped', {'method': 'BDF'}, {}), ('rk45', {}, {}), ('tight', TIGHT, TIGHT),
+                           ('asshipped_cj', {'method': 'BDF', 'jac': 'closed'}, {}),
+                           ('asshipped_ra', {'method': 'BDF', 'reassoc': True}, {})):
         try:
             Xa, Ua, PW, cnt = orc.aux(tg, X, U, Lam, theta, back=back, fwd=fwd, return_counts=True)
         except OracleIntegrationError as e:      # solve_ivp gave up (the reference would crash here): record it
@@ -40,7 +45,10 @@ def run_problem(args):
             PW = np.full((n_grid + 1, n * n + n * r), np.nan); cnt = dict(back_rhs=-1, fwd_rhs=-1)
         loss, dl = orc.loss_grad(taus, wp, tg, X, Xa)
         out['ok_' + tag] = bool(np.isfinite(Xa).all())
-        out['Xa_' + tag] = Xa; out['Ua_' + tag] = Ua; out['loss_' + tag] = loss; out['dl_' + tag] = dl
+        out['loss_' + tag] = loss; out['dl_' + tag] = dl
+        if tag == 'asshipped_ra':
+            continue
+        out['Xa_' + tag] = Xa; out['Ua_' + tag] = Ua
         out['cnt_' + tag] = np.array([cnt['back_rhs'], cnt['fwd_rhs']])
         if tag == 'asshipped':
             out['PW_asshipped'] = PW
