@@ -15,6 +15,7 @@ namespace CPDP_NS {
 struct WsLayout {
     SolveArgs sa;
     double* PW;
+    double* Dbdf;
     size_t bytes;
 };
 
@@ -52,6 +53,7 @@ static WsLayout ws_carve(char* base, int B, int N, int S) {
     a.act = takeI(B);
     a.nact = takeI(1);
     w.PW = takeD(BN1 * NYR);
+    w.Dbdf = takeD((size_t)B * 8 * NYR);      // differences arrays of k_riccati_bdf (BDF_NROWS = 8 rows per problem)
     w.bytes = off;
     return w;
 }
@@ -146,7 +148,7 @@ static int cpdp_aux_impl(void* ws, size_t ws_bytes, int B, int N, int S, double 
     a.B = B; a.N = N; a.T = T; a.theta = theta; a.theta_stride = theta_stride; a.pdata = pdata;
     a.X = X; a.U = U; a.Lam = Lam;
     a.rtol_b = rtol_b; a.atol_b = atol_b; a.rtol_f = rtol_f; a.atol_f = atol_f;
-    a.PW = w.PW; a.Xa = Xa; a.Ua = Ua;
+    a.PW = w.PW; a.Dws = w.Dbdf; a.Xa = Xa; a.Ua = Ua;
     a.W = W; a.D = D;
     for (int i = 0; i < MAX_SEL; ++i) a.sel[i] = (i < D) ? sel_host[i] : 0;
     for (int i = 0; i < D; ++i) if (a.sel[i] < 0 || a.sel[i] >= NX) return -6;
@@ -159,7 +161,7 @@ static int cpdp_aux_impl(void* ws, size_t ws_bytes, int B, int N, int S, double 
             CPDP_PREPARE_SMEM(k_riccati_rk45, ric_bytes);
             CPDP_LAUNCH(k_riccati_rk45, B, AUX_THREADS, ric_bytes, st, a);
         } else {
-            const size_t bdf_bytes = BDF_SMEM_DOUBLES * sizeof(double);
+            const size_t bdf_bytes = BDF_SMEM_BYTES;
             CPDP_PREPARE_SMEM(k_riccati_bdf, bdf_bytes);
             CPDP_LAUNCH(k_riccati_bdf, B, BDF_THREADS, bdf_bytes, st, a);
         }

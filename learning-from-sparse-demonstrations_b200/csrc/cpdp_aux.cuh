@@ -32,6 +32,7 @@ struct AuxArgs {
     const double* X; const double* U; const double* Lam;   // [B][N+1][.]
     double rtol_b, atol_b, rtol_f, atol_f;
     double* PW;            // [B][N+1][NYR]   packed Riccati nodes
+    double* Dws;           // [B][8][NYR]     BDF differences arrays (workspace; mode 1 only)
     double* Xa;            // [B][N+1][NX*NP] aux state nodes  (dx/dtheta)
     double* Ua;            // [B][N+1][NU*NP] aux control nodes
     int W, D;              // waypoints per problem, observed dims
@@ -157,16 +158,16 @@ CPDP_D void riccati_rhs(const AuxShared& s, const double* M, const double* yin, 
     const double* Hxx = M + Model::PMP_HXX; const double* Hxu = M + Model::PMP_HXU; const double* Hxe = M + Model::PMP_HXE;
     const double* Hue = M + Model::PMP_HUE; const double* Hinv = M + Model::PMP_SIZE;
     const double* Wm = yin + NT;
-    for (int i = tid; i < NX * NX; i += nt) {
+    CPDP_LOOP for (int i = tid; i < NX * NX; i += nt) {
         const int r_ = i / NX, c = i % NX;
         s.P[i] = yin[r_ <= c ? tri(r_, c) : tri(c, r_)];
     }
     __syncthreads();
-    for (int i = tid; i < NU * NX + NU * NP; i += nt) {
+    CPDP_LOOP for (int i = tid; i < NU * NX + NU * NP; i += nt) {
         if (i < NU * NX) {
             const int a = i / NX, j = i % NX;
             double acc = Hxu[j * NU + a];
-            for (int p = s.fu_colptr[a]; p < s.fu_colptr[a + 1]; ++p) {
+            CPDP_LOOP for (int p = s.fu_colptr[a]; p < s.fu_colptr[a + 1]; ++p) {
                 const int r_ = s.fu_rowidx[p];
                 acc += fu[r_ * NU + a] * s.P[r_ * NX + j];
             }
@@ -174,7 +175,7 @@ CPDP_D void riccati_rhs(const AuxShared& s, const double* M, const double* yin, 
         } else {
             const int q = i - NU * NX, a = q / NP, k = q % NP;
             double acc = Hue[a * NP + k];
-            for (int p = s.fu_colptr[a]; p < s.fu_colptr[a + 1]; ++p) {
+            CPDP_LOOP for (int p = s.fu_colptr[a]; p < s.fu_colptr[a + 1]; ++p) {
                 const int r_ = s.fu_rowidx[p];
                 acc += fu[r_ * NU + a] * Wm[r_ * NP + k];
             }
@@ -182,42 +183,42 @@ CPDP_D void riccati_rhs(const AuxShared& s, const double* M, const double* yin, 
         }
     }
     __syncthreads();
-    for (int i = tid; i < NU * NX; i += nt) {
+    CPDP_LOOP for (int i = tid; i < NU * NX; i += nt) {
         const int a = i / NX, j = i % NX;
         double acc = 0.0;
-        for (int b2 = 0; b2 < NU; ++b2) acc += Hinv[a * NU + b2] * s.Y[b2 * NX + j];
+        CPDP_LOOP for (int b2 = 0; b2 < NU; ++b2) acc += Hinv[a * NU + b2] * s.Y[b2 * NX + j];
         s.Yp[i] = acc;
     }
     __syncthreads();
-    for (int q = tid; q < NYR; q += nt) {
+    CPDP_LOOP for (int q = tid; q < NYR; q += nt) {
         if (q < NT) {
             const int i = s.ti[q], j = s.tj[q];
             double acc = Hxx[i * NX + j];
-            for (int p = s.fx_colptr[i]; p < s.fx_colptr[i + 1]; ++p) {
+            CPDP_LOOP for (int p = s.fx_colptr[i]; p < s.fx_colptr[i + 1]; ++p) {
                 const int a = s.fx_rowidx[p];
                 acc += fx[a * NX + i] * s.P[a * NX + j];
             }
-            for (int p = s.fx_colptr[j]; p < s.fx_colptr[j + 1]; ++p) {
+            CPDP_LOOP for (int p = s.fx_colptr[j]; p < s.fx_colptr[j + 1]; ++p) {
                 const int a = s.fx_rowidx[p];
                 acc += s.P[i * NX + a] * fx[a * NX + j];
             }
             // symmetric evaluation of Y' Hinv Y: average of (i,j) and (j,i) orderings is not needed because
             // sum_a Y[a][i]*Yp[a][j] and sum_a Yp[a][i]*Y[a][j] agree to rounding; use the mean to be exact-symmetric
             double yy = 0.0;
-            for (int a = 0; a < NU; ++a) yy += 0.5 * (s.Y[a * NX + i] * s.Yp[a * NX + j] + s.Yp[a * NX + i] * s.Y[a * NX + j]);
+            CPDP_LOOP for (int a = 0; a < NU; ++a) yy += 0.5 * (s.Y[a * NX + i] * s.Yp[a * NX + j] + s.Yp[a * NX + i] * s.Y[a * NX + j]);
             ydot[q] = -(acc - yy);
         } else {
             const int e = q - NT, i = e / NP, k = e % NP;
             double acc = -Hxe[i * NP + k];
-            for (int p = s.fx_colptr[i]; p < s.fx_colptr[i + 1]; ++p) {
+            CPDP_LOOP for (int p = s.fx_colptr[i]; p < s.fx_colptr[i + 1]; ++p) {
                 const int a = s.fx_rowidx[p];
                 acc -= fx[a * NX + i] * Wm[a * NP + k];
             }
-            for (int p = s.fe_colptr[k]; p < s.fe_colptr[k + 1]; ++p) {
+            CPDP_LOOP for (int p = s.fe_colptr[k]; p < s.fe_colptr[k + 1]; ++p) {
                 const int a = s.fe_rowidx[p];
                 acc -= s.P[i * NX + a] * fe[a * NP + k];
             }
-            for (int a = 0; a < NU; ++a) acc += s.Yp[a * NX + i] * s.Z[a * NP + k];
+            CPDP_LOOP for (int a = 0; a < NU; ++a) acc += s.Yp[a * NX + i] * s.Z[a * NP + k];
             ydot[q] = acc;
         }
     }
@@ -449,21 +450,25 @@ CPDP_D double* carve(double*& ptr, int n) { double* r_ = ptr; ptr += n; return r
 
 // shared-memory copy of the model's static sparsity tables (divergent lookups are cheap there)
 constexpr int SPTAB_INTS = 2 * (NX + 1) + 2 * Model::FX_nnz + (NX + 1) + (NU + 1) + 2 * Model::FU_nnz + (NP + 1) + Model::FE_nnz + 8;
+// pointers into the table block (pure address arithmetic: folds to constants when `tab` is a constant address)
+CPDP_D void aux_table_ptrs(AuxShared& s, int* tab) {
+    int* p = tab;
+    s.fx_rowptr = p; p += NX + 1; s.fx_colidx = p; p += Model::FX_nnz; s.fx_colptr = p; p += NX + 1; s.fx_rowidx = p; p += Model::FX_nnz;
+    s.fu_rowptr = p; p += NX + 1; s.fu_colidx = p; p += Model::FU_nnz; s.fu_colptr = p; p += NU + 1; s.fu_rowidx = p; p += Model::FU_nnz;
+    s.fe_colptr = p; p += NP + 1; s.fe_rowidx = p; p += Model::FE_nnz;
+}
 CPDP_D void aux_tables(AuxShared& s, int* tab) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    int* p = tab;
-    int* fx_rowptr = p; p += NX + 1; int* fx_colidx = p; p += Model::FX_nnz; int* fx_colptr = p; p += NX + 1; int* fx_rowidx = p; p += Model::FX_nnz;
-    int* fu_rowptr = p; p += NX + 1; int* fu_colidx = p; p += Model::FU_nnz; int* fu_colptr = p; p += NU + 1; int* fu_rowidx = p; p += Model::FU_nnz;
-    int* fe_colptr = p; p += NP + 1; int* fe_rowidx = p; p += Model::FE_nnz;
+    aux_table_ptrs(s, tab);
+    int* fx_rowptr = (int*)s.fx_rowptr; int* fx_colidx = (int*)s.fx_colidx; int* fx_colptr = (int*)s.fx_colptr; int* fx_rowidx = (int*)s.fx_rowidx;
+    int* fu_rowptr = (int*)s.fu_rowptr; int* fu_colidx = (int*)s.fu_colidx; int* fu_colptr = (int*)s.fu_colptr; int* fu_rowidx = (int*)s.fu_rowidx;
+    int* fe_colptr = (int*)s.fe_colptr; int* fe_rowidx = (int*)s.fe_rowidx;
     for (int i = tid; i <= NX; i += nt) { fx_rowptr[i] = Model::FX_rowptr(i); fx_colptr[i] = Model::FX_colptr(i); fu_rowptr[i] = Model::FU_rowptr(i); }
     for (int i = tid; i <= NU; i += nt) fu_colptr[i] = Model::FU_colptr(i);
     for (int i = tid; i <= NP; i += nt) fe_colptr[i] = Model::FE_colptr(i);
     for (int i = tid; i < Model::FX_nnz; i += nt) { fx_colidx[i] = Model::FX_colidx(i); fx_rowidx[i] = Model::FX_rowidx(i); }
     for (int i = tid; i < Model::FU_nnz; i += nt) { fu_colidx[i] = Model::FU_colidx(i); fu_rowidx[i] = Model::FU_rowidx(i); }
     for (int i = tid; i < Model::FE_nnz; i += nt) fe_rowidx[i] = Model::FE_rowidx(i);
-    s.fx_rowptr = fx_rowptr; s.fx_colidx = fx_colidx; s.fx_colptr = fx_colptr; s.fx_rowidx = fx_rowidx;
-    s.fu_rowptr = fu_rowptr; s.fu_colidx = fu_colidx; s.fu_colptr = fu_colptr; s.fu_rowidx = fu_rowidx;
-    s.fe_colptr = fe_colptr; s.fe_rowidx = fe_rowidx;
 }
 
 CPDP_D void aux_shared_common(AuxShared& s, double*& ptr, int* ti, int* tj) {

@@ -22,9 +22,17 @@
 #pragma once
 #include "cpdp_aux.cuh"
 
+// Large, rarely interleaved pieces are kept out of line: the fully inlined kernel was 33 k SASS instructions (535 KB)
+// and its warps spent ~30 % of their stall samples waiting for instruction fetch (ncu, profiles/r01_*schur*).
+#ifdef __CUDACC__
+#define CPDP_D_NOINLINE __device__ __noinline__
+#else
+#define CPDP_D_NOINLINE inline
+#endif
+
 namespace CPDP_NS {
 
-constexpr int BDF_THREADS = 128;
+constexpr int BDF_THREADS = 64;
 constexpr int BDF_MAX_ORDER = 5;
 constexpr int BDF_NEWTON_MAXITER = 4;
 constexpr int BDF_NROWS = BDF_MAX_ORDER + 3;
@@ -35,16 +43,18 @@ struct BdfShared {
     double* Fr; double* Fi;   // [NX*NX]  scratch of the factor / solve steps
     double* Gr; double* Gi;   // [NX*NX]
     double* Dr; double* Di;   // [NT]     1 / ((1/2 + c t_ii) + conj(1/2 + c t_jj))
-    double* Lm;     // [NX*NX]  L at the Jacobian point
+    double* Lm;     // [NX*NX]  L at the Jacobian point            (aliases Fr: dead once bdf_schur has copied it)
     double* Cm;     // [NX*NP]  C at the Jacobian point
-    double* GH;     // [NX*NU]  scratch: fu Huu^{-1}
-    double* Am;     // [NX*NX]  scratch: A
-    double* Rm;     // [NX*NX]  scratch: R
-    double* D;      // [BDF_NROWS][NYR]
-    double* ypred; double* scale; double* psi; double* d; double* y; double* f; double* dy;
+    double* GH;     // [NX*NU]  scratch: fu Huu^{-1}               (aliases Gi)
+    double* Am;     // [NX*NX]  scratch: A                         (aliases Fi)
+    double* Rm;     // [NX*NX]  scratch: R                         (aliases Gr)
+    double* D;      // [BDF_NROWS][NYR]  differences array, GLOBAL memory (L2-resident workspace): element (k, i) is
+                    //                   only ever touched by the thread that owns column i (i % blockDim.x == tid)
+    double* ypred;  // [NYR]  predictor; between intervals it carries the interval's start / end state
+    double* scale; double* psi; double* d; double* y; double* dy;
     double* RU;     // [6*6]
     double* Winv;   // [NX*NX]  inverse of I + c L
-    double* tmp;    // [NYR]    scratch of bdf_solve
+    double* tmp;    // [NYR]    scratch of bdf_solve; f(t0, y0) during the start-up of an interval
     int* flag;      // [2]
 };
 
@@ -53,43 +63,85 @@ CPDP_HD double bdf_gamma(int k) { double g = 0.0; for (int i = 1; i <= k; ++i) g
 CPDP_HD double bdf_alpha(int k) { return (1.0 - bdf_kappa(k)) * bdf_gamma(k); }
 CPDP_HD double bdf_error_const(int k) { return bdf_kappa(k) * bdf_gamma(k) + 1.0 / (k + 1); }
 
+// Shared-memory layout.  Every array sits at a COMPILE-TIME offset of the dynamic shared-memory block, so the
+// out-of-line pieces below rebuild their views from constants (no pointer structs in local memory, no registers).
+constexpr int BDF_SMEM_DOUBLES = MSZ + (2 * NX + NU) + (2 * BDF_THREADS + 2) + NX * NX + 2 * NU * NX + NU * NP   // AuxShared
+                                 + 8 * NX * NX + 2 * NT + NX * NP + NX * NX                                     // Schur data, Cm, Winv
+                                 + 6 * NYR + 36 + 8 + NYR + 2;                                                  // work vectors, RU, tms, tmp, flag
+constexpr int BDF_SMEM_INTS = 2 * NT + SPTAB_INTS;
+constexpr size_t BDF_SMEM_BYTES = (size_t)BDF_SMEM_DOUBLES * sizeof(double) + (size_t)((BDF_SMEM_INTS + 3) & ~3) * sizeof(int);
+static_assert(NX * NU <= NX * NX, "GH aliases an NX x NX scratch matrix");
+
+CPDP_D void bdf_layout(double* smem, AuxShared& s, BdfShared& bs, double*& tms) {
+    double* ptr = smem;
+    s.M = carve(ptr, MSZ);                       // one PMP slot: every Newton iterate of a step shares t_new
+    s.xul = carve(ptr, 2 * NX + NU);
+    s.red = carve(ptr, 2 * BDF_THREADS + 2);
+    s.P = carve(ptr, NX * NX);
+    s.Y = carve(ptr, NU * NX);
+    s.Yp = carve(ptr, NU * NX);
+    s.Z = carve(ptr, NU * NP);
+    bs.Tr = carve(ptr, NX * NX); bs.Ti = carve(ptr, NX * NX); bs.Zr = carve(ptr, NX * NX); bs.Zi = carve(ptr, NX * NX);
+    bs.Fr = carve(ptr, NX * NX); bs.Fi = carve(ptr, NX * NX); bs.Gr = carve(ptr, NX * NX); bs.Gi = carve(ptr, NX * NX);
+    bs.Dr = carve(ptr, NT); bs.Di = carve(ptr, NT);
+    bs.Lm = bs.Fr; bs.Am = bs.Fi; bs.Rm = bs.Gr; bs.GH = bs.Gi;      // Jacobian scratch, dead once bdf_schur has copied Lm
+    bs.Cm = carve(ptr, NX * NP); bs.Winv = carve(ptr, NX * NX);
+    bs.ypred = carve(ptr, NYR); bs.scale = carve(ptr, NYR); bs.psi = carve(ptr, NYR); bs.d = carve(ptr, NYR);
+    bs.y = carve(ptr, NYR); bs.dy = carve(ptr, NYR);
+    bs.RU = carve(ptr, 36);
+    tms = carve(ptr, 8);
+    bs.tmp = carve(ptr, NYR);
+    bs.flag = (int*)carve(ptr, 2);
+    int* ip = (int*)(smem + BDF_SMEM_DOUBLES);
+    s.ti = ip; s.tj = ip + NT;
+    aux_table_ptrs(s, ip + 2 * NT);
+    bs.D = nullptr;
+}
+#define BDF_LAYOUT() CPDP_DYN_SMEM(smem); AuxShared s; BdfShared bs; double* tms; bdf_layout(smem, s, bs, tms); (void)tms
+
+// out-of-line instances of the shared right-hand side / PMP evaluation (one copy each instead of three)
+CPDP_D_NOINLINE void bdf_rhs(const double* yin, double* ydot) { BDF_LAYOUT(); riccati_rhs(s, s.M, yin, ydot); }
+CPDP_D_NOINLINE bool bdf_prepare(const AuxProblem p) { BDF_LAYOUT(); return aux_prepare<false>(s, p, tms, 1); }
+
 // Closed-form Jacobian data at (PMP matrices M, packed state yJ):  L = A' - P R,  C = R W - r_
 // with A = fx - fu Huu^{-1} Hxu', R = fu Huu^{-1} fu', r_ = fe - fu Huu^{-1} Hue  (CPDP.py:262-270).
-CPDP_D void bdf_jacobian(const AuxShared& s, const BdfShared& bs, const double* M, const double* yJ) {
+CPDP_D_NOINLINE void bdf_jacobian(const double* yJ) {
+    BDF_LAYOUT();
+    const double* M = s.M;
     const int tid = threadIdx.x, nt = blockDim.x;
     const double* fx = M + Model::PMP_FX; const double* fu = M + Model::PMP_FU; const double* fe = M + Model::PMP_FE;
     const double* Hxu = M + Model::PMP_HXU; const double* Hue = M + Model::PMP_HUE; const double* Hinv = M + Model::PMP_SIZE;
     const double* Wm = yJ + NT;
     __syncthreads();
-    for (int i = tid; i < NX * NX; i += nt) {
+    CPDP_LOOP for (int i = tid; i < NX * NX; i += nt) {
         const int r_ = i / NX, c = i % NX;
         s.P[i] = yJ[r_ <= c ? tri(r_, c) : tri(c, r_)];
     }
-    for (int i = tid; i < NX * NU; i += nt) {
+    CPDP_LOOP for (int i = tid; i < NX * NU; i += nt) {
         const int r_ = i / NU, a = i % NU;
         double acc = 0.0;
-        for (int b2 = 0; b2 < NU; ++b2) acc += fu[r_ * NU + b2] * Hinv[b2 * NU + a];
+        CPDP_LOOP for (int b2 = 0; b2 < NU; ++b2) acc += fu[r_ * NU + b2] * Hinv[b2 * NU + a];
         bs.GH[i] = acc;
     }
     __syncthreads();
-    for (int i = tid; i < NX * NX; i += nt) {
+    CPDP_LOOP for (int i = tid; i < NX * NX; i += nt) {
         const int r_ = i / NX, c = i % NX;
         double a1 = fx[i], a2 = 0.0;
-        for (int a = 0; a < NU; ++a) { a1 -= bs.GH[r_ * NU + a] * Hxu[c * NU + a]; a2 += bs.GH[r_ * NU + a] * fu[c * NU + a]; }
+        CPDP_LOOP for (int a = 0; a < NU; ++a) { a1 -= bs.GH[r_ * NU + a] * Hxu[c * NU + a]; a2 += bs.GH[r_ * NU + a] * fu[c * NU + a]; }
         bs.Am[i] = a1; bs.Rm[i] = a2;
     }
     __syncthreads();
-    for (int i = tid; i < NX * NX + NX * NP; i += nt) {
+    CPDP_LOOP for (int i = tid; i < NX * NX + NX * NP; i += nt) {
         if (i < NX * NX) {
             const int r_ = i / NX, a = i % NX;
             double acc = bs.Am[a * NX + r_];
-            for (int b2 = 0; b2 < NX; ++b2) acc -= s.P[r_ * NX + b2] * bs.Rm[b2 * NX + a];
+            CPDP_LOOP for (int b2 = 0; b2 < NX; ++b2) acc -= s.P[r_ * NX + b2] * bs.Rm[b2 * NX + a];
             bs.Lm[i] = acc;
         } else {
             const int e = i - NX * NX, r_ = e / NP, k = e % NP;
             double acc = -fe[e];
-            for (int a = 0; a < NU; ++a) acc += bs.GH[r_ * NU + a] * Hue[a * NP + k];
-            for (int b2 = 0; b2 < NX; ++b2) acc += bs.Rm[r_ * NX + b2] * Wm[b2 * NP + k];
+            CPDP_LOOP for (int a = 0; a < NU; ++a) acc += bs.GH[r_ * NU + a] * Hue[a * NP + k];
+            CPDP_LOOP for (int b2 = 0; b2 < NX; ++b2) acc += bs.Rm[r_ * NX + b2] * Wm[b2 * NP + k];
             bs.Cm[e] = acc;
         }
     }
@@ -122,13 +174,13 @@ CPDP_D bool schur_real_w0(double* H, double* Z) {
     if (lane < 32) for (int i = lane; i < n * n; i += 32) Z[i] = (i / n == i % n) ? 1.0 : 0.0;
     CPDP_W0_SYNC();
     // ---- Hessenberg form by Givens rotations in the planes (i-1, i)
-    for (int j = 0; j < n - 2; ++j)
-        for (int i = n - 1; i >= j + 2; --i) {
+    CPDP_LOOP for (int j = 0; j < n - 2; ++j)
+        CPDP_LOOP for (int i = n - 1; i >= j + 2; --i) {
             const double a = h_(i - 1, j), b = h_(i, j);
             if (b == 0.0) continue;
-            const double sc = fabs(a) + fabs(b);
-            const double rr = sc * sqrt((a / sc) * (a / sc) + (b / sc) * (b / sc));
-            const double c = a / rr, s = b / rr;
+            const double sc = fabs(a) + fabs(b), isc = 1.0 / sc;      // reciprocals: one division per dependent stage
+            const double rr = sc * sqrt((a * isc) * (a * isc) + (b * isc) * (b * isc)), irr = 1.0 / rr;
+            const double c = a * irr, s = b * irr;
             CPDP_W0_SYNC();
             if (lane >= j && lane < n) {
                 const double t1 = h_(i - 1, lane), t2 = h_(i, lane);
@@ -149,14 +201,14 @@ CPDP_D bool schur_real_w0(double* H, double* Z) {
             CPDP_W0_SYNC();
         }
     double norm = 0.0;
-    for (int i = 0; i < n; ++i) for (int j = (i > 0 ? i - 1 : 0); j < n; ++j) norm += fabs(h_(i, j));
+    CPDP_LOOP for (int i = 0; i < n; ++i) for (int j = (i > 0 ? i - 1 : 0); j < n; ++j) norm += fabs(h_(i, j));
     // ---- Francis double-shift QR sweeps, full Schur form (rows/columns updated over the whole matrix)
     int en = n - 1;
     while (en >= 0) {
         int its = 0;
         while (true) {
             int l;
-            for (l = en; l >= 1; --l) {
+            CPDP_LOOP for (l = en; l >= 1; --l) {
                 double s = fabs(h_(l - 1, l - 1)) + fabs(h_(l, l));
                 if (s == 0.0) s = norm;
                 if (fabs(h_(l, l - 1)) <= EPS * s) break;
@@ -180,26 +232,27 @@ CPDP_D bool schur_real_w0(double* H, double* Z) {
             ++its;
             int m;
             double p = 0.0, q = 0.0, r = 0.0;
-            for (m = en - 2; m >= l; --m) {
+            CPDP_LOOP for (m = en - 2; m >= l; --m) {
                 const double z = h_(m, m), r0 = x - z, s0 = y - z;
                 p = (r0 * s0 - w) / h_(m + 1, m) + h_(m, m + 1);
                 q = h_(m + 1, m + 1) - z - r0 - s0;
                 r = h_(m + 2, m + 1);
                 const double s = fabs(p) + fabs(q) + fabs(r);
-                if (s != 0.0) { p /= s; q /= s; r /= s; }
+                if (s != 0.0) { const double is = 1.0 / s; p *= is; q *= is; r *= is; }
                 if (m == l) break;
                 const double u = fabs(h_(m, m - 1)) * (fabs(q) + fabs(r));
                 const double v = fabs(p) * (fabs(h_(m - 1, m - 1)) + fabs(z) + fabs(h_(m + 1, m + 1)));
                 if (u <= EPS * v) break;
             }
-            for (int k = m; k <= en - 1; ++k) {
+            CPDP_LOOP for (int k = m; k <= en - 1; ++k) {
                 const bool notlast = (k != en - 1);
                 double x2 = 0.0;
                 if (k != m) {
                     p = h_(k, k - 1); q = h_(k + 1, k - 1); r = notlast ? h_(k + 2, k - 1) : 0.0;
                     x2 = fabs(p) + fabs(q) + fabs(r);
                     if (x2 == 0.0) continue;
-                    p /= x2; q /= x2; r /= x2;
+                    const double ix2 = 1.0 / x2;
+                    p *= ix2; q *= ix2; r *= ix2;
                 }
                 double s = sqrt(p * p + q * q + r * r);
                 if (s == 0.0) continue;
@@ -210,8 +263,9 @@ CPDP_D bool schur_real_w0(double* H, double* Z) {
                     else if (l != m) h_(k, k - 1) = -h_(k, k - 1);
                 }
                 p += s;
-                const double xx = p / s, yy = q / s, zz = r / s;
-                q /= p; r /= p;
+                const double is = 1.0 / s, ip = 1.0 / p;
+                const double xx = p * is, yy = q * is, zz = r * is;
+                q *= ip; r *= ip;
                 if (lane >= k && lane < n) {
                     double pp = h_(k, lane) + q * h_(k + 1, lane);
                     if (notlast) { pp += r * h_(k + 2, lane); h_(k + 2, lane) -= pp * zz; }
@@ -242,11 +296,12 @@ CPDP_D bool schur_real_w0(double* H, double* Z) {
 
 // Complex Schur form L = Z T Z^H from bs.Lm, by warp 0; result in (Tr,Ti), (Zr,Zi).  Returns false (uniformly over
 // the CTA) if the QR iteration did not converge.
-CPDP_D bool bdf_schur(const BdfShared& bs) {
+CPDP_D_NOINLINE bool bdf_schur() {
+    BDF_LAYOUT();
     constexpr int n = NX;
     const int tid = threadIdx.x, nt = blockDim.x;
     __syncthreads();
-    for (int i = tid; i < n * n; i += nt) { bs.Tr[i] = bs.Lm[i]; bs.Ti[i] = 0.0; bs.Zi[i] = 0.0; }
+    CPDP_LOOP for (int i = tid; i < n * n; i += nt) { bs.Tr[i] = bs.Lm[i]; bs.Ti[i] = 0.0; bs.Zi[i] = 0.0; }
     if (tid == 0) bs.flag[0] = 1;
     __syncthreads();
 #ifdef __CUDACC__
@@ -258,7 +313,7 @@ CPDP_D bool bdf_schur(const BdfShared& bs) {
         CPDP_W0_SYNC();
         if (!ok && lane == 0) bs.flag[0] = 0;
         // ---- one unitary rotation per 2 x 2 block:  G = [[c, s], [-conj(s), c]],  T <- G T G^H,  Z <- Z G^H
-        for (int j = 0; ok && j < n - 1; ++j) {
+        CPDP_LOOP for (int j = 0; ok && j < n - 1; ++j) {
             const double cc = bs.Tr[(j + 1) * n + j];
             if (cc == 0.0) continue;
             const double a = bs.Tr[j * n + j], b = bs.Tr[j * n + j + 1], d = bs.Tr[(j + 1) * n + j + 1];
@@ -306,16 +361,17 @@ CPDP_D bool bdf_schur(const BdfShared& bs) {
 }
 
 // scipy's "LU" event for a new c: reciprocals of the Lyapunov pivots and Winv = (I + c L)^{-1} = Re(Z (I + c T)^{-1} Z^H).
-CPDP_D bool bdf_factor(const AuxShared& s, const BdfShared& bs, const double c) {
+CPDP_D_NOINLINE bool bdf_factor(const double c) {
+    BDF_LAYOUT();
     constexpr int n = NX;
     const int tid = threadIdx.x, nt = blockDim.x;
     __syncthreads();
     double bad = 0.0;
     if (tid < n) {                                   // column tid of S = (I + c T)^{-1}  (upper triangular) -> (Fr, Fi)
         const int j = tid;
-        for (int i = j; i >= 0; --i) {
+        CPDP_LOOP for (int i = j; i >= 0; --i) {
             double nr = (i == j) ? 1.0 : 0.0, ni = 0.0;
-            for (int k = i + 1; k <= j; ++k) {
+            CPDP_LOOP for (int k = i + 1; k <= j; ++k) {
                 const double tr = c * bs.Tr[i * n + k], ti = c * bs.Ti[i * n + k];
                 const double sr = bs.Fr[k * n + j], si = bs.Fi[k * n + j];
                 nr -= tr * sr - ti * si;
@@ -327,9 +383,9 @@ CPDP_D bool bdf_factor(const AuxShared& s, const BdfShared& bs, const double c) 
             bs.Fr[i * n + j] = (nr * dr + ni * di) / dd;
             bs.Fi[i * n + j] = (ni * dr - nr * di) / dd;
         }
-        for (int i = j + 1; i < n; ++i) { bs.Fr[i * n + j] = 0.0; bs.Fi[i * n + j] = 0.0; }
+        CPDP_LOOP for (int i = j + 1; i < n; ++i) { bs.Fr[i * n + j] = 0.0; bs.Fi[i * n + j] = 0.0; }
     }
-    for (int q = tid; q < NT; q += nt) {             // 1 / ((1/2 + c t_ii) + conj(1/2 + c t_jj))
+    CPDP_LOOP for (int q = tid; q < NT; q += nt) {             // 1 / ((1/2 + c t_ii) + conj(1/2 + c t_jj))
         const int i = s.ti[q], j = s.tj[q];
         const double dr = 1.0 + c * (bs.Tr[i * n + i] + bs.Tr[j * n + j]), di = c * (bs.Ti[i * n + i] - bs.Ti[j * n + j]);
         const double dd = dr * dr + di * di;
@@ -338,10 +394,10 @@ CPDP_D bool bdf_factor(const AuxShared& s, const BdfShared& bs, const double c) 
     }
     bad = block_reduce(bad, s.red, true);
     if (bad != 0.0) return false;
-    for (int e = tid; e < n * n; e += nt) {          // G = Z S
+    CPDP_LOOP for (int e = tid; e < n * n; e += nt) {          // G = Z S
         const int i = e / n, k = e % n;
         double gr = 0.0, gi = 0.0;
-        for (int j = 0; j <= k; ++j) {
+        CPDP_LOOP for (int j = 0; j <= k; ++j) {
             const double zr = bs.Zr[i * n + j], zi = bs.Zi[i * n + j], sr = bs.Fr[j * n + k], si = bs.Fi[j * n + k];
             gr += zr * sr - zi * si;
             gi += zr * si + zi * sr;
@@ -349,10 +405,10 @@ CPDP_D bool bdf_factor(const AuxShared& s, const BdfShared& bs, const double c) 
         bs.Gr[e] = gr; bs.Gi[e] = gi;
     }
     __syncthreads();
-    for (int e = tid; e < n * n; e += nt) {          // Winv = Re(G Z^H)
+    CPDP_LOOP for (int e = tid; e < n * n; e += nt) {          // Winv = Re(G Z^H)
         const int i = e / n, l = e % n;
         double acc = 0.0;
-        for (int k = 0; k < n; ++k) acc += bs.Gr[i * n + k] * bs.Zr[l * n + k] + bs.Gi[i * n + k] * bs.Zi[l * n + k];
+        CPDP_LOOP for (int k = 0; k < n; ++k) acc += bs.Gr[i * n + k] * bs.Zr[l * n + k] + bs.Gi[i * n + k] * bs.Zi[l * n + k];
         bs.Winv[e] = acc;
     }
     __syncthreads();
@@ -360,24 +416,26 @@ CPDP_D bool bdf_factor(const AuxShared& s, const BdfShared& bs, const double c) 
 }
 
 // dy <- (I - cJ)^{-1} dy   (dy holds the right-hand side on entry; tmp: NYR doubles of scratch)
-CPDP_D void bdf_solve(const AuxShared& s, const BdfShared& bs, const double c, double* dy, double* tmp) {
+CPDP_D_NOINLINE void bdf_solve(const double c) {
+    BDF_LAYOUT();
+    double* dy = bs.dy; double* tmp = bs.tmp;
     constexpr int n = NX;
     const int tid = threadIdx.x, nt = blockDim.x;
     __syncthreads();
-    for (int e = tid; e < n * n; e += nt) {          // F = B Z, B = sym(dy[0:NT])
+    CPDP_LOOP for (int e = tid; e < n * n; e += nt) {          // F = B Z, B = sym(dy[0:NT])
         const int i = e / n, k = e % n;
         double fr = 0.0, fi = 0.0;
-        for (int j = 0; j < n; ++j) {
+        CPDP_LOOP for (int j = 0; j < n; ++j) {
             const double b = dy[i <= j ? tri(i, j) : tri(j, i)];
             fr += b * bs.Zr[j * n + k]; fi += b * bs.Zi[j * n + k];
         }
         bs.Fr[e] = fr; bs.Fi[e] = fi;
     }
     __syncthreads();
-    for (int q = tid; q < NT; q += nt) {             // C = Z^H F (upper triangle) -> (Gr, Gi)
+    CPDP_LOOP for (int q = tid; q < NT; q += nt) {             // C = Z^H F (upper triangle) -> (Gr, Gi)
         const int i = s.ti[q], j = s.tj[q];
         double cr = 0.0, ci = 0.0;
-        for (int k = 0; k < n; ++k) {
+        CPDP_LOOP for (int k = 0; k < n; ++k) {
             const double zr = bs.Zr[k * n + i], zi = bs.Zi[k * n + i], fr = bs.Fr[k * n + j], fi = bs.Fi[k * n + j];
             cr += zr * fr + zi * fi;
             ci += zr * fi - zi * fr;
@@ -392,18 +450,18 @@ CPDP_D void bdf_solve(const AuxShared& s, const BdfShared& bs, const double c, d
 #endif
     {
         const int e = tid >> 2, sub = tid & 3;
-        for (int d = 2 * (n - 1); d >= 0; --d) {
+        CPDP_LOOP for (int d = 2 * (n - 1); d >= 0; --d) {
             const int ilo = (d > n - 1) ? d - (n - 1) : 0;
             const int i = ilo + e, j = d - i;
             const bool valid = (tid < 32) && (i <= j);
             double ar = 0.0, ai = 0.0;
             if (valid) {
-                for (int k = i + 1 + sub; k < n; k += 4) {           // T_ik Y_kj
+                CPDP_LOOP for (int k = i + 1 + sub; k < n; k += 4) {           // T_ik Y_kj
                     const double tr = bs.Tr[i * n + k], ti = bs.Ti[i * n + k], yr = bs.Gr[k * n + j], yi = bs.Gi[k * n + j];
                     ar += tr * yr - ti * yi;
                     ai += tr * yi + ti * yr;
                 }
-                for (int k = j + 1 + sub; k < n; k += 4) {           // Y_ik conj(T_jk)
+                CPDP_LOOP for (int k = j + 1 + sub; k < n; k += 4) {           // Y_ik conj(T_jk)
                     const double tr = bs.Tr[j * n + k], ti = bs.Ti[j * n + k], yr = bs.Gr[i * n + k], yi = bs.Gi[i * n + k];
                     ar += yr * tr + yi * ti;
                     ai += yi * tr - yr * ti;
@@ -432,10 +490,10 @@ CPDP_D void bdf_solve(const AuxShared& s, const BdfShared& bs, const double c, d
         }
     }
     __syncthreads();
-    for (int e = tid; e < n * n; e += nt) {          // F = Z Y
+    CPDP_LOOP for (int e = tid; e < n * n; e += nt) {          // F = Z Y
         const int i = e / n, k = e % n;
         double fr = 0.0, fi = 0.0;
-        for (int j = 0; j < n; ++j) {
+        CPDP_LOOP for (int j = 0; j < n; ++j) {
             const double zr = bs.Zr[i * n + j], zi = bs.Zi[i * n + j], yr = bs.Gr[j * n + k], yi = bs.Gi[j * n + k];
             fr += zr * yr - zi * yi;
             fi += zr * yi + zi * yr;
@@ -443,71 +501,74 @@ CPDP_D void bdf_solve(const AuxShared& s, const BdfShared& bs, const double c, d
         bs.Fr[e] = fr; bs.Fi[e] = fi;
     }
     __syncthreads();
-    for (int q = tid; q < NT; q += nt) {             // X = Re(F Z^H), upper triangle
+    CPDP_LOOP for (int q = tid; q < NT; q += nt) {             // X = Re(F Z^H), upper triangle
         const int i = s.ti[q], l = s.tj[q];
         double acc = 0.0;
-        for (int k = 0; k < n; ++k) acc += bs.Fr[i * n + k] * bs.Zr[l * n + k] + bs.Fi[i * n + k] * bs.Zi[l * n + k];
+        CPDP_LOOP for (int k = 0; k < n; ++k) acc += bs.Fr[i * n + k] * bs.Zr[l * n + k] + bs.Fi[i * n + k] * bs.Zi[l * n + k];
         tmp[q] = acc;
     }
     __syncthreads();
     double* dW = dy + NT;
-    for (int e = tid; e < NX * NP; e += nt) {                  // B_W + c X C
+    CPDP_LOOP for (int e = tid; e < NX * NP; e += nt) {                  // B_W + c X C
         const int i = e / NP, k = e % NP;
         double acc = 0.0;
-        for (int a = 0; a < NX; ++a) acc += tmp[i <= a ? tri(i, a) : tri(a, i)] * bs.Cm[a * NP + k];
+        CPDP_LOOP for (int a = 0; a < NX; ++a) acc += tmp[i <= a ? tri(i, a) : tri(a, i)] * bs.Cm[a * NP + k];
         tmp[NT + e] = dW[e] + c * acc;
     }
-    for (int k = tid; k < NT; k += nt) dy[k] = tmp[k];
+    CPDP_LOOP for (int k = tid; k < NT; k += nt) dy[k] = tmp[k];
     __syncthreads();
-    for (int e = tid; e < NX * NP; e += nt) {                  // dW = (I + cL)^{-1} (...)
+    CPDP_LOOP for (int e = tid; e < NX * NP; e += nt) {                  // dW = (I + cL)^{-1} (...)
         const int i = e / NP, k = e % NP;
         double acc = 0.0;
-        for (int a = 0; a < NX; ++a) acc += bs.Winv[i * NX + a] * tmp[NT + a * NP + k];
+        CPDP_LOOP for (int a = 0; a < NX; ++a) acc += bs.Winv[i * NX + a] * tmp[NT + a * NP + k];
         dW[e] = acc;
     }
     __syncthreads();
 }
 
 // change_D (bdf.py:18-33): D[:order+1] <- (R U)' D[:order+1]
-CPDP_D void bdf_change_D(const BdfShared& bs, const int order, const double factor) {
+CPDP_D_NOINLINE void bdf_change_D(double* D, const int order, const double factor) {
+    BDF_LAYOUT();
+    bs.D = D;
     const int tid = threadIdx.x, nt = blockDim.x;
     __syncthreads();
     if (tid == 0) {
         double R[6][6], U[6][6];
-        for (int j = 0; j <= order; ++j) { R[0][j] = 1.0; U[0][j] = 1.0; }
-        for (int i = 1; i <= order; ++i) {
+        CPDP_LOOP for (int j = 0; j <= order; ++j) { R[0][j] = 1.0; U[0][j] = 1.0; }
+        CPDP_LOOP for (int i = 1; i <= order; ++i) {
             R[i][0] = 0.0; U[i][0] = 0.0;
-            for (int j = 1; j <= order; ++j) {
+            CPDP_LOOP for (int j = 1; j <= order; ++j) {
                 R[i][j] = R[i - 1][j] * (((double)(i - 1) - factor * j) / i);
                 U[i][j] = U[i - 1][j] * (((double)(i - 1) - (double)j) / i);
             }
         }
-        for (int i = 0; i <= order; ++i)
-            for (int j = 0; j <= order; ++j) {
+        CPDP_LOOP for (int i = 0; i <= order; ++i)
+            CPDP_LOOP for (int j = 0; j <= order; ++j) {
                 double acc = 0.0;
-                for (int k = 0; k <= order; ++k) acc += R[i][k] * U[k][j];
+                CPDP_LOOP for (int k = 0; k <= order; ++k) acc += R[i][k] * U[k][j];
                 bs.RU[i * 6 + j] = acc;
             }
     }
     __syncthreads();
-    for (int q = tid; q < NYR; q += nt) {
+    CPDP_LOOP for (int q = tid; q < NYR; q += nt) {
         double v[6], o[6];
-        for (int i = 0; i <= order; ++i) v[i] = bs.D[(size_t)i * NYR + q];
-        for (int i = 0; i <= order; ++i) {
+        CPDP_LOOP for (int i = 0; i <= order; ++i) v[i] = bs.D[(size_t)i * NYR + q];
+        CPDP_LOOP for (int i = 0; i <= order; ++i) {
             double acc = 0.0;
-            for (int j = 0; j <= order; ++j) acc += bs.RU[j * 6 + i] * v[j];
+            CPDP_LOOP for (int j = 0; j <= order; ++j) acc += bs.RU[j * 6 + i] * v[j];
             o[i] = acc;
         }
-        for (int i = 0; i <= order; ++i) bs.D[(size_t)i * NYR + q] = o[i];
+        CPDP_LOOP for (int i = 0; i <= order; ++i) bs.D[(size_t)i * NYR + q] = o[i];
     }
     __syncthreads();
 }
 
 // RMS norm of v/scale over the FULL (n^2 + n r) state (off-diagonal entries of the packed P count twice)
-CPDP_D double bdf_norm(const AuxShared& s, const double* v, const double* scale, const double mul) {
+CPDP_D_NOINLINE double bdf_norm(const double* v, const double* scale, const double mul) {
+    BDF_LAYOUT();
     const int tid = threadIdx.x, nt = blockDim.x;
     double a = 0.0;
-    for (int i = tid; i < NYR; i += nt) { const double x = mul * v[i] / scale[i]; a += ric_wgt(s, i) * x * x; }
+    CPDP_LOOP for (int i = tid; i < NYR; i += nt) { const double x = mul * v[i] / scale[i]; a += ric_wgt(s, i) * x * x; }
     return sqrt(block_reduce(a, s.red, false) / (double)NFULL_R);
 }
 
@@ -518,34 +579,34 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
     const int tid = threadIdx.x, nt = blockDim.x;
     const double dir = (t1 >= t0) ? 1.0 : -1.0;
     const double EPS = 2.220446049250313e-16;
-    double* M0 = s.M;                  // PMP matrices of the current evaluation time (single slot)
     // ---- __init__ (bdf.py:200-257)
     if (tid == 0) tms[0] = t0;
-    if (!aux_prepare<false>(s, p, tms, 1)) return 2;
-    riccati_rhs(s, M0, y, bs.f); ++cnt[0];
-    bdf_jacobian(s, bs, M0, y); ++cnt[3];
-    if (!bdf_schur(bs)) return 4;
+    if (!bdf_prepare(p)) return 2;
+    double* f0 = bs.tmp;               // f(t0, y0): bdf_solve (the other user of tmp) is not called during start-up
+    bdf_rhs(y, f0); ++cnt[0];
+    bdf_jacobian(y); ++cnt[3];
+    if (!bdf_schur()) return 4;
     double h_abs;
     {
         const double interval_length = fabs(t1 - t0);
         double a0 = 0.0, a1 = 0.0;
-        for (int i = tid; i < NYR; i += nt) {
+        CPDP_LOOP for (int i = tid; i < NYR; i += nt) {
             const double sc = atol + fabs(y[i]) * rtol;
             a0 += ric_wgt(s, i) * (y[i] / sc) * (y[i] / sc);
-            a1 += ric_wgt(s, i) * (bs.f[i] / sc) * (bs.f[i] / sc);
+            a1 += ric_wgt(s, i) * (f0[i] / sc) * (f0[i] / sc);
         }
         const double d0 = sqrt(block_reduce(a0, s.red, false) / (double)NFULL_R);
         const double d1 = sqrt(block_reduce(a1, s.red, false) / (double)NFULL_R);
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         h0 = fmin(h0, interval_length);
-        for (int i = tid; i < NYR; i += nt) bs.ypred[i] = y[i] + h0 * dir * bs.f[i];
+        CPDP_LOOP for (int i = tid; i < NYR; i += nt) bs.y[i] = y[i] + h0 * dir * f0[i];
         if (tid == 0) tms[0] = t0 + h0 * dir;
-        if (!aux_prepare<false>(s, p, tms, 1)) return 2;
-        riccati_rhs(s, M0, bs.ypred, bs.dy); ++cnt[0];
+        if (!bdf_prepare(p)) return 2;
+        bdf_rhs(bs.y, bs.dy); ++cnt[0];
         double a2 = 0.0;
-        for (int i = tid; i < NYR; i += nt) {
+        CPDP_LOOP for (int i = tid; i < NYR; i += nt) {
             const double sc = atol + fabs(y[i]) * rtol;
-            const double v = (bs.dy[i] - bs.f[i]) / sc;
+            const double v = (bs.dy[i] - f0[i]) / sc;
             a2 += ric_wgt(s, i) * v * v;
         }
         const double d2 = sqrt(block_reduce(a2, s.red, false) / (double)NFULL_R) / h0;
@@ -555,7 +616,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
         h_abs = fmin(fmin(100 * h0, h1), interval_length);
     }
     const double newton_tol = fmax(10 * EPS / rtol, fmin(0.03, sqrt(rtol)));
-    for (int i = tid; i < NYR; i += nt) { bs.D[i] = y[i]; bs.D[NYR + i] = bs.f[i] * h_abs * dir; }
+    CPDP_LOOP for (int i = tid; i < NYR; i += nt) { bs.D[i] = y[i]; bs.D[NYR + i] = f0[i] * h_abs * dir; }
     __syncthreads();
     int order = 1, n_equal_steps = 0;
     bool lu_valid = false;
@@ -566,7 +627,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
         // ---- _step_impl (bdf.py:314-453)
         const double min_step = 10 * fabs(nextafter(t, dir * INFINITY) - t);
         if (h_abs < min_step) {
-            bdf_change_D(bs, order, min_step / h_abs);
+            bdf_change_D(bs.D, order, min_step / h_abs);
             h_abs = min_step;
             n_equal_steps = 0;
         }
@@ -579,52 +640,53 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
             t_new = t + h;
             if (dir * (t_new - t1) > 0) {
                 t_new = t1;
-                bdf_change_D(bs, order, fabs(t_new - t) / h_abs);
+                bdf_change_D(bs.D, order, fabs(t_new - t) / h_abs);
                 n_equal_steps = 0;
                 lu_valid = false;
             }
             h = t_new - t;
             h_abs = fabs(h);
             double gam[6];
-            for (int k = 1; k <= order; ++k) gam[k] = bdf_gamma(k);
+            CPDP_LOOP for (int k = 1; k <= order; ++k) gam[k] = bdf_gamma(k);
             const double al = bdf_alpha(order);
-            for (int i = tid; i < NYR; i += nt) {
+            CPDP_LOOP for (int i = tid; i < NYR; i += nt) {
                 double yp = 0.0, ps = 0.0;
-                for (int k = 0; k <= order; ++k) yp += bs.D[(size_t)k * NYR + i];
-                for (int k = 1; k <= order; ++k) ps += bs.D[(size_t)k * NYR + i] * gam[k];
+                CPDP_LOOP for (int k = 0; k <= order; ++k) yp += bs.D[(size_t)k * NYR + i];
+                CPDP_LOOP for (int k = 1; k <= order; ++k) ps += bs.D[(size_t)k * NYR + i] * gam[k];
                 bs.ypred[i] = yp;
                 bs.scale[i] = atol + rtol * fabs(yp);
                 bs.psi[i] = ps / al;
             }
             if (tid == 0) tms[0] = t_new;
-            if (!aux_prepare<false>(s, p, tms, 1)) return 2;      // PMP matrices at t_new (every Newton iterate shares them)
+            if (!bdf_prepare(p)) return 2;      // PMP matrices at t_new (every Newton iterate shares them)
             const double c = h / al;
             bool converged = false;
             while (!converged) {
                 if (!lu_valid) {
-                    if (!bdf_factor(s, bs, c)) return 4;
+                    if (!bdf_factor(c)) return 4;
                     lu_valid = true; c_lu = c; ++cnt[2];
                 }
                 // ---- solve_bdf_system (bdf.py:36-75)
-                for (int i = tid; i < NYR; i += nt) { bs.d[i] = 0.0; bs.y[i] = bs.ypred[i]; }
+                CPDP_LOOP for (int i = tid; i < NYR; i += nt) { bs.d[i] = 0.0; bs.y[i] = bs.ypred[i]; }
                 __syncthreads();
                 double dy_norm_old = -1.0;
                 int k = 0;
-                for (k = 0; k < BDF_NEWTON_MAXITER; ++k) {
-                    riccati_rhs(s, M0, bs.y, bs.f); ++cnt[0];
+                CPDP_LOOP for (k = 0; k < BDF_NEWTON_MAXITER; ++k) {
+                    bdf_rhs(bs.y, bs.dy); ++cnt[0];
                     double fin = 0.0;
-                    for (int i = tid; i < NYR; i += nt) {
-                        if (!(fabs(bs.f[i]) < 1e300)) fin = 1.0;
-                        bs.dy[i] = c * bs.f[i] - bs.psi[i] - bs.d[i];
+                    CPDP_LOOP for (int i = tid; i < NYR; i += nt) {
+                        const double fv = bs.dy[i];
+                        if (!(fabs(fv) < 1e300)) fin = 1.0;
+                        bs.dy[i] = c * fv - bs.psi[i] - bs.d[i];
                     }
                     fin = block_reduce(fin, s.red, true);
                     if (fin != 0.0) break;
-                    bdf_solve(s, bs, c_lu, bs.dy, bs.tmp);
-                    const double dy_norm = bdf_norm(s, bs.dy, bs.scale, 1.0);
+                    bdf_solve(c_lu);
+                    const double dy_norm = bdf_norm(bs.dy, bs.scale, 1.0);
                     const bool have_rate = dy_norm_old >= 0.0;
                     const double rate = have_rate ? dy_norm / dy_norm_old : 0.0;
                     if (have_rate && (rate >= 1 || pow(rate, (double)(BDF_NEWTON_MAXITER - k)) / (1 - rate) * dy_norm > newton_tol)) break;
-                    for (int i = tid; i < NYR; i += nt) { bs.y[i] += bs.dy[i]; bs.d[i] += bs.dy[i]; }
+                    CPDP_LOOP for (int i = tid; i < NYR; i += nt) { bs.y[i] += bs.dy[i]; bs.d[i] += bs.dy[i]; }
                     __syncthreads();
                     if (dy_norm == 0 || (have_rate && rate / (1 - rate) * dy_norm < newton_tol)) { converged = true; break; }
                     dy_norm_old = dy_norm;
@@ -632,28 +694,28 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                 n_iter = (k < BDF_NEWTON_MAXITER) ? k + 1 : BDF_NEWTON_MAXITER;
                 if (!converged) {
                     if (current_jac) break;
-                    bdf_jacobian(s, bs, M0, bs.ypred); ++cnt[3];
-                    if (!bdf_schur(bs)) return 4;
+                    bdf_jacobian(bs.ypred); ++cnt[3];
+                    if (!bdf_schur()) return 4;
                     lu_valid = false;
                     current_jac = true;
                 }
             }
             if (!converged) {
                 h_abs *= 0.5;
-                bdf_change_D(bs, order, 0.5);
+                bdf_change_D(bs.D, order, 0.5);
                 n_equal_steps = 0;
                 lu_valid = false;
                 continue;
             }
             safety = 0.9 * (2 * BDF_NEWTON_MAXITER + 1) / (double)(2 * BDF_NEWTON_MAXITER + n_iter);
-            for (int i = tid; i < NYR; i += nt) bs.scale[i] = atol + rtol * fabs(bs.y[i]);
+            CPDP_LOOP for (int i = tid; i < NYR; i += nt) bs.scale[i] = atol + rtol * fabs(bs.y[i]);
             __syncthreads();
-            error_norm = bdf_norm(s, bs.d, bs.scale, bdf_error_const(order));
+            error_norm = bdf_norm(bs.d, bs.scale, bdf_error_const(order));
             if (!(error_norm == error_norm)) return 2;
             if (error_norm > 1) {
                 const double factor = fmax(0.2, safety * pow(error_norm, -1.0 / (order + 1)));
                 h_abs *= factor;
-                bdf_change_D(bs, order, factor);
+                bdf_change_D(bs.D, order, factor);
                 n_equal_steps = 0;
                 // LU deliberately kept (bdf.py:404-405)
             } else {
@@ -664,17 +726,17 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
         ++cnt[1];
         t = t_new;
         // ---- update the differences (bdf.py:417-421)
-        for (int i = tid; i < NYR; i += nt) {
+        CPDP_LOOP for (int i = tid; i < NYR; i += nt) {
             const double dv = bs.d[i];
             bs.D[(size_t)(order + 2) * NYR + i] = dv - bs.D[(size_t)(order + 1) * NYR + i];
             bs.D[(size_t)(order + 1) * NYR + i] = dv;
-            for (int k = order; k >= 0; --k) bs.D[(size_t)k * NYR + i] += bs.D[(size_t)(k + 1) * NYR + i];
+            CPDP_LOOP for (int k = order; k >= 0; --k) bs.D[(size_t)k * NYR + i] += bs.D[(size_t)(k + 1) * NYR + i];
         }
         __syncthreads();
         if (n_equal_steps < order + 1) continue;
         double error_m_norm = INFINITY, error_p_norm = INFINITY;
-        if (order > 1) error_m_norm = bdf_norm(s, bs.D + (size_t)order * NYR, bs.scale, bdf_error_const(order - 1));
-        if (order < BDF_MAX_ORDER) error_p_norm = bdf_norm(s, bs.D + (size_t)(order + 2) * NYR, bs.scale, bdf_error_const(order + 1));
+        if (order > 1) error_m_norm = bdf_norm(bs.D + (size_t)order * NYR, bs.scale, bdf_error_const(order - 1));
+        if (order < BDF_MAX_ORDER) error_p_norm = bdf_norm(bs.D + (size_t)(order + 2) * NYR, bs.scale, bdf_error_const(order + 1));
         const double fm = pow(error_m_norm, -1.0 / order);
         const double f0 = pow(error_norm, -1.0 / (order + 1));
         const double fp = pow(error_p_norm, -1.0 / (order + 2));
@@ -684,91 +746,67 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
         order += delta_order;
         const double factor = fmin(10.0, safety * fmaxv);
         h_abs *= factor;
-        bdf_change_D(bs, order, factor);
+        bdf_change_D(bs.D, order, factor);
         n_equal_steps = 0;
         lu_valid = false;
     }
     // solve_ivp(t_eval=[t1]) returns the dense output at the step end = D[0] (bdf.py:462-484)
-    for (int i = tid; i < NYR; i += nt) y[i] = bs.D[i];
+    CPDP_LOOP for (int i = tid; i < NYR; i += nt) y[i] = bs.D[i];
     __syncthreads();
     return 0;
 }
 
-constexpr int BDF_SMEM_DOUBLES = MSZ + (2 * NX + NU) + (2 * BDF_THREADS + 2) + NX * NX + 2 * NU * NX + NU * NP
-                                 + 8 * NX * NX + 2 * NT + 4 * NX * NX + NX * NP + NX * NU + BDF_NROWS * NYR + 7 * NYR + 36 + 8 + NYR
-                                 + NYR + 2;
-
 // k_riccati_bdf: backward sweep of COCSys.auxSysSolver as shipped (CPDP.py:327-338).
-CPDP_GLOBAL void __launch_bounds__(BDF_THREADS) k_riccati_bdf(AuxArgs a) {
-    CPDP_DYN_SMEM(smem);
-    CPDP_SHARED int s_ti[NT], s_tj[NT], s_tab[SPTAB_INTS];
-    CPDP_SHARED double s_hxx[NX * NX], s_hxe[NX * NP];
+CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, 6) k_riccati_bdf(AuxArgs a) {
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     if (a.solve_status && (a.solve_status[b] == ST_NUMERIC || a.solve_status[b] == ST_RUNNING)) {
         if (tid == 0) a.aux_status[b] = 3;
         return;
     }
-    double* ptr = smem;
-    AuxShared s;
-    s.M = carve(ptr, MSZ);                       // one PMP slot: every Newton iterate of a step shares t_new
-    s.xul = carve(ptr, 2 * NX + NU);
-    s.red = carve(ptr, 2 * BDF_THREADS + 2);
-    s.P = carve(ptr, NX * NX);
-    s.Y = carve(ptr, NU * NX);
-    s.Yp = carve(ptr, NU * NX);
-    s.Z = carve(ptr, NU * NP);
-    s.ti = s_ti; s.tj = s_tj;
-    for (int q = tid; q < NT; q += nt) {
-        int i = 0, rem = q;
-        while (rem >= NX - i) { rem -= NX - i; ++i; }
-        s_ti[q] = i; s_tj[q] = i + rem;
+    BDF_LAYOUT();
+    {
+        int* s_ti = (int*)s.ti; int* s_tj = (int*)s.tj;
+        CPDP_LOOP for (int q = tid; q < NT; q += nt) {
+            int i = 0, rem = q;
+            while (rem >= NX - i) { rem -= NX - i; ++i; }
+            s_ti[q] = i; s_tj[q] = i + rem;
+        }
     }
-    for (int q = tid; q < MSZ; q += nt) s.M[q] = 0.0;
-    aux_tables(s, s_tab);
-    BdfShared bs;
-    bs.Tr = carve(ptr, NX * NX); bs.Ti = carve(ptr, NX * NX); bs.Zr = carve(ptr, NX * NX); bs.Zi = carve(ptr, NX * NX);
-    bs.Fr = carve(ptr, NX * NX); bs.Fi = carve(ptr, NX * NX); bs.Gr = carve(ptr, NX * NX); bs.Gi = carve(ptr, NX * NX);
-    bs.Dr = carve(ptr, NT); bs.Di = carve(ptr, NT);
-    bs.Lm = carve(ptr, NX * NX); bs.Am = carve(ptr, NX * NX);
-    bs.Rm = carve(ptr, NX * NX); bs.Cm = carve(ptr, NX * NP); bs.GH = carve(ptr, NX * NU);
-    bs.D = carve(ptr, BDF_NROWS * NYR);
-    bs.ypred = carve(ptr, NYR); bs.scale = carve(ptr, NYR); bs.psi = carve(ptr, NYR); bs.d = carve(ptr, NYR);
-    bs.y = carve(ptr, NYR); bs.f = carve(ptr, NYR); bs.dy = carve(ptr, NYR);
-    bs.RU = carve(ptr, 36);
-    double* tms = carve(ptr, 8);
-    double* y = carve(ptr, NYR);
-    bs.Winv = carve(ptr, NX * NX); bs.tmp = carve(ptr, NYR);
-    bs.flag = (int*)carve(ptr, 2);
+    CPDP_LOOP for (int q = tid; q < MSZ; q += nt) s.M[q] = 0.0;
+    aux_tables(s, (int*)s.ti + 2 * NT);
+    bs.D = a.Dws + (size_t)b * BDF_NROWS * NYR;
+    double* y = bs.ypred;                        // state at the interval boundaries (the predictor is dead there)
     const int N = a.N;
     AuxProblem p;
     p.X = a.X + (size_t)b * (N + 1) * NX; p.U = a.U + (size_t)b * (N + 1) * NU; p.Lam = a.Lam + (size_t)b * (N + 1) * NX;
     p.th = a.theta + (size_t)b * a.theta_stride; p.pd = a.pdata + (size_t)b * NQ; p.PW = nullptr; p.dt = a.T / N; p.N = N;
     double* PW = a.PW + (size_t)b * (N + 1) * NYR;
+    double* s_hxx = bs.Fr; double* s_hxe = bs.dy;     // terminal condition staged in scratch (NX*NX and NX*NP doubles)
     if (tid == 0) {
         const double tN = p.dt * N;
         double xT[NX];
         const int lo = interp_lo(tN, p.dt, N);
-        for (int i = 0; i < NX; ++i) xT[i] = interp_val(p.X[(size_t)lo * NX + i], p.X[(size_t)(lo + 1) * NX + i], p.dt * lo, p.dt * (lo + 1), tN);
+        CPDP_LOOP for (int i = 0; i < NX; ++i) xT[i] = interp_val(p.X[(size_t)lo * NX + i], p.X[(size_t)(lo + 1) * NX + i], p.dt * lo, p.dt * (lo + 1), tN);
         Model::term2(xT, p.th, p.pd, s_hxx, s_hxe);
     }
     __syncthreads();
-    for (int q = tid; q < NYR; q += nt) {
-        const double v = (q < NT) ? 0.5 * (s_hxx[s_ti[q] * NX + s_tj[q]] + s_hxx[s_tj[q] * NX + s_ti[q]]) : s_hxe[q - NT];
+    CPDP_LOOP for (int q = tid; q < NYR; q += nt) {
+        const double v = (q < NT) ? 0.5 * (s_hxx[s.ti[q] * NX + s.tj[q]] + s_hxx[s.tj[q] * NX + s.ti[q]]) : s_hxe[q - NT];
         y[q] = v;
         PW[(size_t)N * NYR + q] = v;
     }
     __syncthreads();
     int cnt[4] = {0, 0, 0, 0};
     int st = 0;
-    for (int k = N; k >= 1 && st == 0; --k) {
+    CPDP_LOOP for (int k = N; k >= 1 && st == 0; --k) {
         st = bdf_interval(s, bs, p, p.dt * k, p.dt * (k - 1), a.rtol_b, a.atol_b, y, tms, cnt);
-        for (int q = tid; q < NYR; q += nt) PW[(size_t)(k - 1) * NYR + q] = y[q];
+        CPDP_LOOP for (int q = tid; q < NYR; q += nt) PW[(size_t)(k - 1) * NYR + q] = y[q];
         __syncthreads();
     }
 #ifdef CPDP_DEBUG_DUMP
     if (st == 4) {
         double* dst = a.Xa + (size_t)b * (N + 1) * NYF;
-        for (int i = tid; i < NX * NX; i += nt) {
+        CPDP_LOOP for (int i = tid; i < NX * NX; i += nt) {
             dst[i] = bs.Lm[i]; dst[NX * NX + i] = bs.Tr[i]; dst[2 * NX * NX + i] = bs.Ti[i];
             dst[3 * NX * NX + i] = bs.Zr[i]; dst[4 * NX * NX + i] = bs.Zi[i];
         }

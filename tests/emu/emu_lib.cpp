@@ -52,31 +52,23 @@ static void emu_launch(F kernel, int grid, int block, size_t smem, Args... args)
 #ifdef CPDP_WITH_BDF
 namespace CPDP_NS {
 void k_emu_bdf_linear(const double* L, const double* Cm, double c, const double* rhs, double* out_TZ, double* out_sol, int* ok) {
-    CPDP_DYN_SMEM(smem);
-    CPDP_SHARED int s_ti[NT], s_tj[NT];
     const int tid = threadIdx.x, nt = blockDim.x;
-    double* ptr = smem;
-    AuxShared s;
-    s.red = carve(ptr, 2 * BDF_THREADS + 2);
-    s.ti = s_ti; s.tj = s_tj;
-    for (int q = tid; q < NT; q += nt) {
-        int i = 0, rem = q;
-        while (rem >= NX - i) { rem -= NX - i; ++i; }
-        s_ti[q] = i; s_tj[q] = i + rem;
+    BDF_LAYOUT();
+    {
+        int* s_ti = (int*)s.ti; int* s_tj = (int*)s.tj;
+        for (int q = tid; q < NT; q += nt) {
+            int i = 0, rem = q;
+            while (rem >= NX - i) { rem -= NX - i; ++i; }
+            s_ti[q] = i; s_tj[q] = i + rem;
+        }
     }
-    BdfShared bs;
-    bs.Tr = carve(ptr, NX * NX); bs.Ti = carve(ptr, NX * NX); bs.Zr = carve(ptr, NX * NX); bs.Zi = carve(ptr, NX * NX);
-    bs.Fr = carve(ptr, NX * NX); bs.Fi = carve(ptr, NX * NX); bs.Gr = carve(ptr, NX * NX); bs.Gi = carve(ptr, NX * NX);
-    bs.Dr = carve(ptr, NT); bs.Di = carve(ptr, NT); bs.Lm = carve(ptr, NX * NX); bs.Cm = carve(ptr, NX * NP);
-    bs.Winv = carve(ptr, NX * NX); bs.tmp = carve(ptr, NYR); bs.dy = carve(ptr, NYR);
-    bs.flag = (int*)carve(ptr, 2);
     for (int i = tid; i < NX * NX; i += nt) bs.Lm[i] = L[i];
     for (int i = tid; i < NX * NP; i += nt) bs.Cm[i] = Cm[i];
     for (int i = tid; i < NYR; i += nt) bs.dy[i] = rhs[i];
     __syncthreads();
-    bool good = bdf_schur(bs);
-    if (good) good = bdf_factor(s, bs, c);
-    if (good) bdf_solve(s, bs, c, bs.dy, bs.tmp);
+    bool good = bdf_schur();
+    if (good) good = bdf_factor(c);
+    if (good) bdf_solve(c);
     __syncthreads();
     for (int i = tid; i < NX * NX; i += nt) {
         out_TZ[i] = bs.Tr[i]; out_TZ[NX * NX + i] = bs.Ti[i]; out_TZ[2 * NX * NX + i] = bs.Zr[i]; out_TZ[3 * NX * NX + i] = bs.Zi[i];
@@ -89,7 +81,7 @@ void k_emu_bdf_linear(const double* L, const double* Cm, double c, const double*
 
 extern "C" CPDP_API int cpdp_emu_bdf_linear(const double* L, const double* Cm, double c, const double* rhs, double* out_TZ, double* out_sol) {
     int ok = 0;
-    emu_launch(CPDP_NS::k_emu_bdf_linear, 1, CPDP_NS::BDF_THREADS, (size_t)(16 * CPDP_NS::NX * CPDP_NS::NX + 8 * CPDP_NS::NYR + 1024) * sizeof(double),
+    emu_launch(CPDP_NS::k_emu_bdf_linear, 1, CPDP_NS::BDF_THREADS, CPDP_NS::BDF_SMEM_BYTES,
                L, Cm, c, rhs, out_TZ, out_sol, &ok);
     return ok;
 }
