@@ -155,7 +155,7 @@ static int cpdp_aux_impl(void* ws, size_t ws_bytes, int B, int N, int S, double 
     a.taus = taus; a.taus_stride = taus_stride; a.wp = wp;
     a.loss = loss; a.dtheta = dtheta; a.solve_status = solve_status; a.aux_status = aux_status; a.counters = counters;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t ric_bytes = RIC_SMEM_DOUBLES * sizeof(double), fwd_bytes = FWD_SMEM_DOUBLES * sizeof(double);
+    const size_t ric_bytes = rk_smem_bytes<false>(), fwd_bytes = rk_smem_bytes<true>();
     if (phases & 1) {
         if (mode == 0) {
             CPDP_PREPARE_SMEM(k_riccati_rk45, ric_bytes);

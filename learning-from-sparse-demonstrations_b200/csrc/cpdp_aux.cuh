@@ -136,9 +136,9 @@ struct AuxProblem {
 CPDP_D bool pmp_at(const AuxProblem& p, double t, double* xul, double* M) {
     const int lo = interp_lo(t, p.dt, p.N);
     const double xlo = p.dt * lo, xhi = p.dt * (lo + 1);
-    for (int i = 0; i < NX; ++i) xul[i] = interp_val(p.X[(size_t)lo * NX + i], p.X[(size_t)(lo + 1) * NX + i], xlo, xhi, t);
-    for (int i = 0; i < NU; ++i) xul[NX + i] = interp_val(p.U[(size_t)lo * NU + i], p.U[(size_t)(lo + 1) * NU + i], xlo, xhi, t);
-    for (int i = 0; i < NX; ++i) xul[NX + NU + i] = interp_val(p.Lam[(size_t)lo * NX + i], p.Lam[(size_t)(lo + 1) * NX + i], xlo, xhi, t);
+    CPDP_LOOP for (int i = 0; i < NX; ++i) xul[i] = interp_val(p.X[(size_t)lo * NX + i], p.X[(size_t)(lo + 1) * NX + i], xlo, xhi, t);
+    CPDP_LOOP for (int i = 0; i < NU; ++i) xul[NX + i] = interp_val(p.U[(size_t)lo * NU + i], p.U[(size_t)(lo + 1) * NU + i], xlo, xhi, t);
+    CPDP_LOOP for (int i = 0; i < NX; ++i) xul[NX + NU + i] = interp_val(p.Lam[(size_t)lo * NX + i], p.Lam[(size_t)(lo + 1) * NX + i], xlo, xhi, t);
     Model::pmp(xul, xul + NX, xul + NX + NU, p.th, p.pd, M);
     return inv_small<NU>(M + Model::PMP_HUU, M + Model::PMP_SIZE);
 }
@@ -234,21 +234,21 @@ CPDP_D void forward_rhs(const AuxShared& s, int slot, const double* Xin, double*
     const double* M = s.M + (size_t)slot * MSZ;
     const double* fx = M + Model::PMP_FX; const double* fu = M + Model::PMP_FU; const double* fe = M + Model::PMP_FE;
     const double* HY = s.HY + (size_t)slot * NU * NX; const double* HZ = s.HZ + (size_t)slot * NU * NP;
-    for (int i = tid; i < NU * NP; i += nt) {
+    CPDP_LOOP for (int i = tid; i < NU * NP; i += nt) {
         const int a = i / NP, k = i % NP;
         double acc = HZ[i];
-        for (int c = 0; c < NX; ++c) acc += HY[a * NX + c] * Xin[c * NP + k];
+        CPDP_LOOP for (int c = 0; c < NX; ++c) acc += HY[a * NX + c] * Xin[c * NP + k];
         s.Uc[i] = acc;
     }
     __syncthreads();
-    for (int q = tid; q < NYF; q += nt) {
+    CPDP_LOOP for (int q = tid; q < NYF; q += nt) {
         const int i = q / NP, k = q % NP;
         double acc = fe[q];
-        for (int p = s.fx_rowptr[i]; p < s.fx_rowptr[i + 1]; ++p) {
+        CPDP_LOOP for (int p = s.fx_rowptr[i]; p < s.fx_rowptr[i + 1]; ++p) {
             const int a = s.fx_colidx[p];
             acc += fx[i * NX + a] * Xin[a * NP + k];
         }
-        for (int p = s.fu_rowptr[i]; p < s.fu_rowptr[i + 1]; ++p) {
+        CPDP_LOOP for (int p = s.fu_rowptr[i]; p < s.fu_rowptr[i + 1]; ++p) {
             const int a = s.fu_colidx[p];
             acc += fu[i * NU + a] * s.Uc[a * NP + k];
         }
@@ -267,7 +267,7 @@ CPDP_D bool aux_prepare(const AuxShared& s, const AuxProblem& p, const double* t
         if (!pmp_at(p, times[tid], s.xul + (size_t)tid * (2 * NX + NU), s.M + (size_t)tid * MSZ)) bad = 1.0;
     }
     if (FWD) {
-        for (int q = tid; q < cnt * NYR; q += nt) {
+        CPDP_LOOP for (int q = tid; q < cnt * NYR; q += nt) {
             const int sl = q / NYR, e = q % NYR;
             const double t = times[sl];
             const int lo = interp_lo(t, p.dt, p.N);
@@ -278,7 +278,7 @@ CPDP_D bool aux_prepare(const AuxShared& s, const AuxProblem& p, const double* t
     if (bad != 0.0) return false;
     if (FWD) {
         // Y = fu'P + Hux ; Z = fu'W + Hue   (stored temporarily in HY/HZ), then multiplied by -Hinv
-        for (int q = tid; q < cnt * (NU * NX + NU * NP); q += nt) {
+        CPDP_LOOP for (int q = tid; q < cnt * (NU * NX + NU * NP); q += nt) {
             const int sl = q / (NU * NX + NU * NP), i = q % (NU * NX + NU * NP);
             const double* M = s.M + (size_t)sl * MSZ;
             const double* fu = M + Model::PMP_FU;
@@ -286,7 +286,7 @@ CPDP_D bool aux_prepare(const AuxShared& s, const AuxProblem& p, const double* t
             if (i < NU * NX) {
                 const int a = i / NX, j = i % NX;
                 double acc = M[Model::PMP_HXU + j * NU + a];
-                for (int pp = s.fu_colptr[a]; pp < s.fu_colptr[a + 1]; ++pp) {
+                CPDP_LOOP for (int pp = s.fu_colptr[a]; pp < s.fu_colptr[a + 1]; ++pp) {
                     const int r_ = s.fu_rowidx[pp];
                     acc += fu[r_ * NU + a] * PWt[r_ <= j ? tri(r_, j) : tri(j, r_)];
                 }
@@ -294,7 +294,7 @@ CPDP_D bool aux_prepare(const AuxShared& s, const AuxProblem& p, const double* t
             } else {
                 const int e = i - NU * NX, a = e / NP, k = e % NP;
                 double acc = M[Model::PMP_HUE + a * NP + k];
-                for (int pp = s.fu_colptr[a]; pp < s.fu_colptr[a + 1]; ++pp) {
+                CPDP_LOOP for (int pp = s.fu_colptr[a]; pp < s.fu_colptr[a + 1]; ++pp) {
                     const int r_ = s.fu_rowidx[pp];
                     acc += fu[r_ * NU + a] * PWt[NT + r_ * NP + k];
                 }
@@ -303,15 +303,15 @@ CPDP_D bool aux_prepare(const AuxShared& s, const AuxProblem& p, const double* t
         }
         __syncthreads();
         // in-place multiply by -Hinv, one thread per (slot, column)
-        for (int q = tid; q < cnt * (NX + NP); q += nt) {
+        CPDP_LOOP for (int q = tid; q < cnt * (NX + NP); q += nt) {
             const int sl = q / (NX + NP), c = q % (NX + NP);
             const double* Hinv = s.M + (size_t)sl * MSZ + Model::PMP_SIZE;
             double col[NU], out[NU];
             if (c < NX) { for (int a = 0; a < NU; ++a) col[a] = s.HY[(size_t)sl * NU * NX + a * NX + c]; }
             else { for (int a = 0; a < NU; ++a) col[a] = s.HZ[(size_t)sl * NU * NP + a * NP + (c - NX)]; }
-            for (int a = 0; a < NU; ++a) {
+            CPDP_LOOP for (int a = 0; a < NU; ++a) {
                 double acc = 0.0;
-                for (int b2 = 0; b2 < NU; ++b2) acc += Hinv[a * NU + b2] * col[b2];
+                CPDP_LOOP for (int b2 = 0; b2 < NU; ++b2) acc += Hinv[a * NU + b2] * col[b2];
                 out[a] = -acc;
             }
             if (c < NX) { for (int a = 0; a < NU; ++a) s.HY[(size_t)sl * NU * NX + a * NX + c] = out[a]; }
@@ -322,123 +322,10 @@ CPDP_D bool aux_prepare(const AuxShared& s, const AuxProblem& p, const double* t
     return true;
 }
 
-// ------------------------------------------------------------------------------------------------
-// RK45 over one grid interval [t0, t1] (either direction), scipy semantics.  y (in/out), K[7][NY] and the work
-// vectors live in shared memory.  Returns 0 ok, 1 step too small, 2 non-finite.
-// ------------------------------------------------------------------------------------------------
-template <bool FWD, int NY>
-CPDP_D int rk45_interval(const AuxShared& s, const AuxProblem& p, double t0, double t1, double rtol, double atol,
-                         double* y, double* yn, double* ys, double* K, double* tms, int& nrhs, int& nsteps) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const double dir = (t1 >= t0) ? 1.0 : -1.0;
-    const double NF = FWD ? (double)NYF : (double)NFULL_R;
-    auto rhs = [&](int slot, const double* yin, double* yout) {
-        if (FWD) forward_rhs(s, slot, yin, yout);
-        else riccati_rhs(s, s.M + (size_t)slot * MSZ, yin, yout);
-        ++nrhs;
-    };
-    auto wgt = [&](int i) { return FWD ? 1.0 : ric_wgt(s, i); };
-    double* f = K;                       // K[0] holds f(t, y)
-    // f0
-    if (tid == 0) tms[0] = t0;
-    if (!aux_prepare<FWD>(s, p, tms, 1)) return 2;
-    rhs(0, y, f);
-    // select_initial_step (common.py:68-134), order = 4
-    double h_abs;
-    {
-        const double interval_length = fabs(t1 - t0);
-        double a0 = 0.0, a1 = 0.0;
-        for (int i = tid; i < NY; i += nt) {
-            const double sc = atol + fabs(y[i]) * rtol;
-            a0 += wgt(i) * (y[i] / sc) * (y[i] / sc);
-            a1 += wgt(i) * (f[i] / sc) * (f[i] / sc);
-        }
-        const double d0 = sqrt(block_reduce(a0, s.red, false) / NF);
-        const double d1 = sqrt(block_reduce(a1, s.red, false) / NF);
-        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        h0 = fmin(h0, interval_length);
-        for (int i = tid; i < NY; i += nt) ys[i] = y[i] + h0 * dir * f[i];
-        if (tid == 0) tms[0] = t0 + h0 * dir;
-        if (!aux_prepare<FWD>(s, p, tms, 1)) return 2;
-        rhs(0, ys, yn);                   // f1 in yn
-        double a2 = 0.0;
-        for (int i = tid; i < NY; i += nt) {
-            const double sc = atol + fabs(y[i]) * rtol;
-            const double v = (yn[i] - f[i]) / sc;
-            a2 += wgt(i) * v * v;
-        }
-        const double d2 = sqrt(block_reduce(a2, s.red, false) / NF) / h0;
-        double h1;
-        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
-        else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
-        h_abs = fmin(fmin(100 * h0, h1), interval_length);
-    }
-    double t = t0;
-    while (dir * (t - t1) < 0) {
-        const double min_step = 10 * fabs(nextafter(t, dir * INFINITY) - t);
-        if (h_abs < min_step) h_abs = min_step;
-        bool rejected = false;
-        double t_new = t;
-        while (true) {
-            if (h_abs < min_step) return 1;
-            double h = h_abs * dir;
-            t_new = t + h;
-            if (dir * (t_new - t1) > 0) t_new = t1;
-            h = t_new - t;
-            h_abs = fabs(h);
-            __syncthreads();
-            if (tid < NSLOT) tms[tid] = t + dp_C(tid + 1) * h;
-            if (!aux_prepare<FWD>(s, p, tms, NSLOT)) return 2;
-            for (int st = 1; st < 6; ++st) {
-                for (int i = tid; i < NY; i += nt) {
-                    double acc = 0.0;
-                    for (int j = 0; j < st; ++j) acc += K[(size_t)j * NY + i] * dp_A(st, j);
-                    ys[i] = y[i] + acc * h;
-                }
-                __syncthreads();
-                rhs(dp_slot(st), ys, K + (size_t)st * NY);
-            }
-            for (int i = tid; i < NY; i += nt) {
-                double acc = 0.0;
-                for (int j = 0; j < 6; ++j) acc += K[(size_t)j * NY + i] * dp_B(j);
-                yn[i] = y[i] + h * acc;
-            }
-            __syncthreads();
-            rhs(4, yn, K + (size_t)6 * NY);
-            double ae = 0.0, fin = 0.0;
-            for (int i = tid; i < NY; i += nt) {
-                double acc = 0.0;
-                for (int j = 0; j < 7; ++j) acc += K[(size_t)j * NY + i] * dp_E(j);
-                const double sc = atol + fmax(fabs(y[i]), fabs(yn[i])) * rtol;
-                const double v = acc * h / sc;
-                ae += wgt(i) * v * v;
-                if (!(fabs(yn[i]) < 1e300)) fin = 1.0;
-            }
-            const double error_norm = sqrt(block_reduce(ae, s.red, false) / NF);
-            fin = block_reduce(fin, s.red, true);
-            if (fin != 0.0 || !(error_norm == error_norm)) return 2;
-            ++nsteps;
-            if (error_norm < 1) {
-                double factor = (error_norm == 0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -0.2));
-                if (rejected) factor = fmin(1.0, factor);
-                h_abs *= factor;
-                break;
-            }
-            h_abs *= fmax(0.2, 0.9 * pow(error_norm, -0.2));
-            rejected = true;
-        }
-        t = t_new;
-        for (int i = tid; i < NY; i += nt) { y[i] = yn[i]; K[i] = K[(size_t)6 * NY + i]; }
-        __syncthreads();
-    }
-    return 0;
-}
-
 // dynamic shared memory carve-up ---------------------------------------------------------------------
-constexpr int RIC_SMEM_DOUBLES = NSLOT * MSZ + NSLOT * (2 * NX + NU) + (AUX_THREADS + 1) + NX * NX + 2 * NU * NX + NU * NP
-                                 + 3 * NYR + 7 * NYR + 8;
-constexpr int FWD_SMEM_DOUBLES = NSLOT * MSZ + NSLOT * (2 * NX + NU) + (AUX_THREADS + 1) + NX * NX + 2 * NU * NX + NU * NP
-                                 + NSLOT * NYR + NSLOT * NU * NX + NSLOT * NU * NP + NU * NP + 3 * NYF + 7 * NYF + 8;
+constexpr int RK_COMMON_DOUBLES = NSLOT * MSZ + NSLOT * (2 * NX + NU) + (AUX_THREADS + 1) + NX * NX + 2 * NU * NX + NU * NP;
+constexpr int RIC_SMEM_DOUBLES = RK_COMMON_DOUBLES + 3 * NYR + 7 * NYR + 8;
+constexpr int FWD_SMEM_DOUBLES = RK_COMMON_DOUBLES + NSLOT * NYR + NSLOT * NU * NX + NSLOT * NU * NP + NU * NP + 3 * NYF + 7 * NYF + 8;
 
 #ifdef __CUDACC__
 #define CPDP_DYN_SMEM(name) extern __shared__ __align__(16) double name[]
@@ -471,7 +358,17 @@ CPDP_D void aux_tables(AuxShared& s, int* tab) {
     for (int i = tid; i < Model::FE_nnz; i += nt) fe_rowidx[i] = Model::FE_rowidx(i);
 }
 
-CPDP_D void aux_shared_common(AuxShared& s, double*& ptr, int* ti, int* tj) {
+// Shared-memory layout of the RK45 kernels: every array at a compile-time offset of the dynamic block (doubles first,
+// then the int tables), so that the out-of-line pieces rebuild their views from constants.
+struct RkWork { double* y; double* yn; double* ys; double* K; double* tms; };
+constexpr int AUX_SMEM_INTS = 2 * NT + SPTAB_INTS;
+template <bool FWD> constexpr size_t rk_smem_bytes() {
+    return (size_t)(FWD ? FWD_SMEM_DOUBLES : RIC_SMEM_DOUBLES) * sizeof(double) + (size_t)((AUX_SMEM_INTS + 3) & ~3) * sizeof(int);
+}
+template <bool FWD>
+CPDP_D void rk_layout(double* smem, AuxShared& s, RkWork& w) {
+    constexpr int NY = FWD ? NYF : NYR;
+    double* ptr = smem;
     s.M = carve(ptr, NSLOT * MSZ);
     s.xul = carve(ptr, NSLOT * (2 * NX + NU));
     s.red = carve(ptr, AUX_THREADS + 1);
@@ -479,23 +376,160 @@ CPDP_D void aux_shared_common(AuxShared& s, double*& ptr, int* ti, int* tj) {
     s.Y = carve(ptr, NU * NX);
     s.Yp = carve(ptr, NU * NX);
     s.Z = carve(ptr, NU * NP);
-    s.ti = ti; s.tj = tj;
+    if (FWD) {
+        s.PWt = carve(ptr, NSLOT * NYR); s.HY = carve(ptr, NSLOT * NU * NX); s.HZ = carve(ptr, NSLOT * NU * NP);
+        s.Uc = carve(ptr, NU * NP);
+    } else {
+        s.PWt = nullptr; s.HY = nullptr; s.HZ = nullptr; s.Uc = nullptr;
+    }
+    w.y = carve(ptr, NY); w.yn = carve(ptr, NY); w.ys = carve(ptr, NY);
+    w.K = carve(ptr, 7 * NY); w.tms = carve(ptr, 8);
+    int* ip = (int*)(smem + (FWD ? FWD_SMEM_DOUBLES : RIC_SMEM_DOUBLES));
+    s.ti = ip; s.tj = ip + NT;
+    aux_table_ptrs(s, ip + 2 * NT);
+}
+#define RK_LAYOUT(FWD) CPDP_DYN_SMEM(smem); AuxShared s; RkWork w; rk_layout<FWD>(smem, s, w)
+
+// fills ti/tj and the sparsity tables, clears the structural zeros of the PMP slots (all threads; caller syncs)
+CPDP_D void aux_shared_fill(const AuxShared& s) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int q = tid; q < NT; q += nt) {
+    int* ti = (int*)s.ti; int* tj = (int*)s.tj;
+    CPDP_LOOP for (int q = tid; q < NT; q += nt) {
         int i = 0, rem = q;
         while (rem >= NX - i) { rem -= NX - i; ++i; }
         ti[q] = i; tj[q] = i + rem;
     }
-    for (int q = tid; q < NSLOT * MSZ; q += nt) s.M[q] = 0.0;     // structural zeros of the PMP matrices
+    CPDP_LOOP for (int q = tid; q < NSLOT * MSZ; q += nt) s.M[q] = 0.0;     // structural zeros of the PMP matrices
+}
+
+// ------------------------------------------------------------------------------------------------
+// RK45 over one grid interval [t0, t1] (either direction), scipy semantics.  y (in/out), K[7][NY] and the work
+// vectors live in shared memory.  Returns 0 ok, 1 step too small, 2 non-finite.
+// ------------------------------------------------------------------------------------------------
+// out-of-line pieces (one copy each per kernel; see the instruction-cache note in cpdp_bdf.cuh)
+template <bool FWD>
+CPDP_D_NOINLINE bool rk_prepare(const AuxProblem p, int cnt) {
+    RK_LAYOUT(FWD);
+    return aux_prepare<FWD>(s, p, w.tms, cnt);
+}
+template <bool FWD>
+CPDP_D_NOINLINE void rk_rhs(int slot, const double* yin, double* yout) {
+    RK_LAYOUT(FWD);
+    if (FWD) forward_rhs(s, slot, yin, yout);
+    else riccati_rhs(s, s.M + (size_t)slot * MSZ, yin, yout);
+}
+
+template <bool FWD, int NY>
+CPDP_D int rk45_interval(const AuxShared& s, const AuxProblem& p, double t0, double t1, double rtol, double atol,
+                         double* y, double* yn, double* ys, double* K, double* tms, int& nrhs, int& nsteps) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double dir = (t1 >= t0) ? 1.0 : -1.0;
+    const double NF = FWD ? (double)NYF : (double)NFULL_R;
+    auto rhs = [&](int slot, const double* yin, double* yout) {
+        rk_rhs<FWD>(slot, yin, yout);
+        ++nrhs;
+    };
+    auto wgt = [&](int i) { return FWD ? 1.0 : ric_wgt(s, i); };
+    double* f = K;                       // K[0] holds f(t, y)
+    // f0
+    if (tid == 0) tms[0] = t0;
+    if (!rk_prepare<FWD>(p, 1)) return 2;
+    rhs(0, y, f);
+    // select_initial_step (common.py:68-134), order = 4
+    double h_abs;
+    {
+        const double interval_length = fabs(t1 - t0);
+        double a0 = 0.0, a1 = 0.0;
+        CPDP_LOOP for (int i = tid; i < NY; i += nt) {
+            const double sc = atol + fabs(y[i]) * rtol;
+            a0 += wgt(i) * (y[i] / sc) * (y[i] / sc);
+            a1 += wgt(i) * (f[i] / sc) * (f[i] / sc);
+        }
+        const double d0 = sqrt(block_reduce(a0, s.red, false) / NF);
+        const double d1 = sqrt(block_reduce(a1, s.red, false) / NF);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, interval_length);
+        CPDP_LOOP for (int i = tid; i < NY; i += nt) ys[i] = y[i] + h0 * dir * f[i];
+        if (tid == 0) tms[0] = t0 + h0 * dir;
+        if (!rk_prepare<FWD>(p, 1)) return 2;
+        rhs(0, ys, yn);                   // f1 in yn
+        double a2 = 0.0;
+        CPDP_LOOP for (int i = tid; i < NY; i += nt) {
+            const double sc = atol + fabs(y[i]) * rtol;
+            const double v = (yn[i] - f[i]) / sc;
+            a2 += wgt(i) * v * v;
+        }
+        const double d2 = sqrt(block_reduce(a2, s.red, false) / NF) / h0;
+        double h1;
+        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+        else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
+        h_abs = fmin(fmin(100 * h0, h1), interval_length);
+    }
+    double t = t0;
+    while (dir * (t - t1) < 0) {
+        const double min_step = 10 * fabs(nextafter(t, dir * INFINITY) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false;
+        double t_new = t;
+        while (true) {
+            if (h_abs < min_step) return 1;
+            double h = h_abs * dir;
+            t_new = t + h;
+            if (dir * (t_new - t1) > 0) t_new = t1;
+            h = t_new - t;
+            h_abs = fabs(h);
+            __syncthreads();
+            if (tid < NSLOT) tms[tid] = t + dp_C(tid + 1) * h;
+            if (!rk_prepare<FWD>(p, NSLOT)) return 2;
+            CPDP_LOOP for (int st = 1; st < 6; ++st) {
+                CPDP_LOOP for (int i = tid; i < NY; i += nt) {
+                    double acc = 0.0;
+                    CPDP_LOOP for (int j = 0; j < st; ++j) acc += K[(size_t)j * NY + i] * dp_A(st, j);
+                    ys[i] = y[i] + acc * h;
+                }
+                __syncthreads();
+                rhs(dp_slot(st), ys, K + (size_t)st * NY);
+            }
+            CPDP_LOOP for (int i = tid; i < NY; i += nt) {
+                double acc = 0.0;
+                CPDP_LOOP for (int j = 0; j < 6; ++j) acc += K[(size_t)j * NY + i] * dp_B(j);
+                yn[i] = y[i] + h * acc;
+            }
+            __syncthreads();
+            rhs(4, yn, K + (size_t)6 * NY);
+            double ae = 0.0, fin = 0.0;
+            CPDP_LOOP for (int i = tid; i < NY; i += nt) {
+                double acc = 0.0;
+                CPDP_LOOP for (int j = 0; j < 7; ++j) acc += K[(size_t)j * NY + i] * dp_E(j);
+                const double sc = atol + fmax(fabs(y[i]), fabs(yn[i])) * rtol;
+                const double v = acc * h / sc;
+                ae += wgt(i) * v * v;
+                if (!(fabs(yn[i]) < 1e300)) fin = 1.0;
+            }
+            const double error_norm = sqrt(block_reduce(ae, s.red, false) / NF);
+            fin = block_reduce(fin, s.red, true);
+            if (fin != 0.0 || !(error_norm == error_norm)) return 2;
+            ++nsteps;
+            if (error_norm < 1) {
+                double factor = (error_norm == 0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -0.2));
+                if (rejected) factor = fmin(1.0, factor);
+                h_abs *= factor;
+                break;
+            }
+            h_abs *= fmax(0.2, 0.9 * pow(error_norm, -0.2));
+            rejected = true;
+        }
+        t = t_new;
+        CPDP_LOOP for (int i = tid; i < NY; i += nt) { y[i] = yn[i]; K[i] = K[(size_t)6 * NY + i]; }
+        __syncthreads();
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_riccati_rk45: backward sweep, P(T)=hxx, W(T)=hxe, RK45 per interval (CPDP.py:327-336 with method RK45).
 // ------------------------------------------------------------------------------------------------
 CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
-    CPDP_DYN_SMEM(smem);
-    CPDP_SHARED int s_ti[NT], s_tj[NT], s_tab[SPTAB_INTS];
-    CPDP_SHARED double s_hxx[NX * NX], s_hxe[NX * NP];
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     // The reference never looks at IPOPT's return status (CPDP.py:183); here trajectories that are not a solution
     // at all (NaN / still iterating) are skipped and flagged, max-iter / line-search exits are integrated as they are.
@@ -503,12 +537,11 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
         if (tid == 0) a.aux_status[b] = 3;
         return;
     }
-    double* ptr = smem;
-    AuxShared s;
-    aux_shared_common(s, ptr, s_ti, s_tj);
-    aux_tables(s, s_tab);
-    double* y = carve(ptr, NYR); double* yn = carve(ptr, NYR); double* ys = carve(ptr, NYR);
-    double* K = carve(ptr, 7 * NYR); double* tms = carve(ptr, 8);
+    RK_LAYOUT(false);
+    aux_shared_fill(s);
+    aux_tables(s, (int*)s.ti + 2 * NT);
+    double* y = w.y; double* yn = w.yn; double* ys = w.ys; double* K = w.K; double* tms = w.tms;
+    double* s_hxx = K; double* s_hxe = K + NX * NX;       // terminal condition staged in the (still unused) stage array
     const int N = a.N;
     AuxProblem p;
     p.X = a.X + (size_t)b * (N + 1) * NX; p.U = a.U + (size_t)b * (N + 1) * NU; p.Lam = a.Lam + (size_t)b * (N + 1) * NX;
@@ -525,7 +558,7 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
     }
     __syncthreads();
     for (int q = tid; q < NYR; q += nt) {
-        const double v = (q < NT) ? 0.5 * (s_hxx[s_ti[q] * NX + s_tj[q]] + s_hxx[s_tj[q] * NX + s_ti[q]]) : s_hxe[q - NT];
+        const double v = (q < NT) ? 0.5 * (s_hxx[s.ti[q] * NX + s.tj[q]] + s_hxx[s.tj[q] * NX + s.ti[q]]) : s_hxe[q - NT];
         y[q] = v;
         PW[(size_t)N * NYR + q] = v;
     }
@@ -544,22 +577,16 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
 //   L = sum_i |wp_i - y(x(tau_i))|^2 ,  dL = sum_i (y - wp_i)' Sel X(tau_i)   (no factor 2, as in the reference).
 // ------------------------------------------------------------------------------------------------
 CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_aux_forward(AuxArgs a) {
-    CPDP_DYN_SMEM(smem);
-    CPDP_SHARED int s_ti[NT], s_tj[NT], s_tab[SPTAB_INTS];
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     if (a.aux_status[b] != 0) {
         if (tid == 0) a.loss[b] = 0.0;
         for (int i = tid; i < NP; i += nt) a.dtheta[(size_t)b * NP + i] = 0.0;
         return;
     }
-    double* ptr = smem;
-    AuxShared s;
-    aux_shared_common(s, ptr, s_ti, s_tj);
-    aux_tables(s, s_tab);
-    s.PWt = carve(ptr, NSLOT * NYR); s.HY = carve(ptr, NSLOT * NU * NX); s.HZ = carve(ptr, NSLOT * NU * NP);
-    s.Uc = carve(ptr, NU * NP);
-    double* y = carve(ptr, NYF); double* yn = carve(ptr, NYF); double* ys = carve(ptr, NYF);
-    double* K = carve(ptr, 7 * NYF); double* tms = carve(ptr, 8);
+    RK_LAYOUT(true);
+    aux_shared_fill(s);
+    aux_tables(s, (int*)s.ti + 2 * NT);
+    double* y = w.y; double* yn = w.yn; double* ys = w.ys; double* K = w.K; double* tms = w.tms;
     const int N = a.N;
     AuxProblem p;
     p.X = a.X + (size_t)b * (N + 1) * NX; p.U = a.U + (size_t)b * (N + 1) * NU; p.Lam = a.Lam + (size_t)b * (N + 1) * NX;
@@ -572,7 +599,7 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_aux_forward(AuxArgs a) {
     for (int k = 0; k <= N && st == 0; ++k) {
         // aux control at node k
         if (tid == 0) tms[0] = p.dt * k;
-        if (!aux_prepare<true>(s, p, tms, 1)) { st = 2; break; }
+        if (!rk_prepare<true>(p, 1)) { st = 2; break; }
         for (int i = tid; i < NU * NP; i += nt) {
             const int aa = i / NP, kk = i % NP;
             double acc = s.HZ[i];

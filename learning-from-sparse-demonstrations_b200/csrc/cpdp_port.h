@@ -17,6 +17,7 @@
 #define CPDP_LOOP _Pragma("unroll 1")
 #define CPDP_HD __host__ __device__ __forceinline__
 #define CPDP_D __device__ __forceinline__
+#define CPDP_D_NOINLINE __device__ __noinline__
 #define CPDP_GLOBAL __global__
 #define CPDP_SHARED __shared__
 #else
@@ -27,6 +28,7 @@
 #define CPDP_LOOP
 #define CPDP_HD inline
 #define CPDP_D inline
+#define CPDP_D_NOINLINE inline
 #define CPDP_GLOBAL
 #define CPDP_SHARED static
 #define __restrict__ __restrict

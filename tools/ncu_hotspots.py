@@ -3,6 +3,7 @@
 usage: ncu_hotspots.py report.ncu-rep [kernel-substring] [top]"""
 import collections
 import os
+import re
 import sys
 
 sys.path.insert(0, "/opt/nvidia/nsight-compute/2025.2.1/extras/python")
@@ -55,7 +56,29 @@ def main():
             print("%-22s %4d inst %5.1f%% smp %5.1f%% | bar %3.0f%% ssb %3.0f%% wait %3.0f%% noinst %3.0f%% sel %3.0f%% | %s" % (
                 fn, ln, 100 * v["inst"] / tot_i, 100 * s / max(tot_s, 1), 100 * v["barrier"] / max(s, 1), 100 * v["short_scoreboard"] / max(s, 1),
                 100 * v["wait"] / max(s, 1), 100 * v["no_instructions"] / max(s, 1), 100 * v["selected"] / max(s, 1), text))
-        # per-function aggregation
+        # per-function aggregation (function = nearest preceding line that looks like a CPDP_* function header)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        agg = collections.defaultdict(lambda: [0.0, 0.0, 0.0])
+        heads = {}
+        for (fn, ln), v in by.items():
+            if fn not in heads:
+                cand = [os.path.join(dp, fn) for dp, _, fs in os.walk(root) if fn in fs]
+                hs = []
+                if cand:
+                    for i, line in enumerate(open(cand[0]).read().split("\n"), 1):
+                        m = re.match(r"^\s*(?:template.*>\s*)?CPDP_(?:D|HD|GLOBAL|D_NOINLINE)\b.*?(\w+)\s*\(", line)
+                        if m:
+                            hs.append((i, m.group(1)))
+                heads[fn] = hs
+            name = fn
+            for i, nm in heads[fn]:
+                if i <= ln:
+                    name = nm
+            a = agg[name]
+            a[0] += v["inst"]; a[1] += sum(v[nm] for nm in names); a[2] += v["barrier"]
+        print("--- by function")
+        for name, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            print("%-28s inst %5.1f%%  samples %5.1f%%  (barrier part %5.1f%%)" % (name, 100 * a[0] / tot_i, 100 * a[1] / max(tot_s, 1), 100 * a[2] / max(tot_s, 1)))
         return
 
 
