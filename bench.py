@@ -80,13 +80,13 @@ def _cpu_one(job):
 
 def cpu_baseline(n_grid, sample, steps=1, warmup=0, max_workers=0, deadline_s=240.0):
     """Oracle (the CPU restatement of the reference algorithm) on a bounded sample of the same synthetic batch, one
-    process per host core.  Each step maps `sample` OCPs (default: one per worker) over the pool; the run stops
+    process per host core.  Each step maps `sample` OCPs (default: four per worker) over the pool; the run stops
     taking new steps after `deadline_s`.  Returns (cpu_baseline dict, seconds, steps done)."""
     from multiprocessing import Pool
     from lfsd_b200 import synthetic
     cores = os.cpu_count() or 1
     workers = min(cores, max_workers) if max_workers else cores
-    sample = sample or workers
+    sample = sample or 4 * workers          # ~10-15 s of CPU work on the box's cores
     workers = min(workers, sample)
     qb = synthetic.quad_batch(max(sample, 1))
     jobs = [(qb["x0"][b], qb["goal"][b], qb["theta"], qb["taus"], qb["wp"][b]) for b in range(sample)]
@@ -183,11 +183,17 @@ def flop_model(info, n, m, r, N, S, iters_sum, B, cnt, mode):
         + 4 * (nt + n * r)
     ny_r, ny_f = nt + n * r, n * r
     if mode == "bdf":
-        # per rhs evaluation: Riccati rhs + Newton residual/solve (packed LU triangular solves + W block) + norms;
-        # per step: PMP matrices at t_new, predictor/psi/difference update; per LU: packed (nt) and n x n factorisations
-        back = cnt[0] * (ric + 2 * nt * nt + 2 * n * n * r + 2 * n * n * r + 8 * ny_r) \
-            + cnt[1] * (pmp + 30 * ny_r) + cnt[4] * (2.0 / 3 * nt ** 3 + 2.0 / 3 * n ** 3 + 4 * n * nt) \
-            + cnt[5] * (2 * n * n * m * 2 + 2 * n ** 3 + 2 * n * n * r)
+        # k_riccati_bdf as built: one real Schur form per Jacobian, Bartels-Stewart solves.
+        # per rhs evaluation (= Newton iteration): Riccati rhs, two-sided real transforms (2 n^3 + 2 nt n each way), block
+        #   rotations, the complex triangular Lyapunov sweep (8 flops per complex multiply-add), W block, norms/updates;
+        # per accepted step: PMP matrices at t_new, predictor / psi / difference update, change_D;
+        # per "LU" event (new c): (I + cT)^-1 by back substitution, pivots, rotation, two n^3 products;
+        # per Jacobian: closed-form L, C, Givens-Hessenberg + Francis QR with vectors (~25 n^3 + 10/3 n^3, LAPACK count)
+        sweep_macs = sum((n - 1 - i) + (n - 1 - j) for i in range(n) for j in range(i, n))
+        solve_bs = 2 * (2 * n ** 3 + 2 * nt * n) + 2 * 16 * nt + 8 * sweep_macs + 10 * nt + 4 * n * n * r
+        back = cnt[0] * (ric + solve_bs + 8 * ny_r) \
+            + cnt[1] * (pmp + 30 * ny_r) + cnt[4] * (4.0 / 3 * n ** 3 + 10 * nt + 16 * n * n + 4 * n ** 3) \
+            + cnt[5] * (2 * n * n * m * 2 + 2 * n ** 3 + 2 * n * n * r + 25 * n ** 3 + 10.0 / 3 * n ** 3)
     else:
         back = cnt[0] * (ric + pmp * 6.0 / 7 + 16 * ny_r)
     fwdf = cnt[2] * (fwd + 16 * ny_f)
@@ -345,6 +351,16 @@ def run_ours(a):
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # DRAM traffic of the dominant kernel: taken from the committed `ncu --set full` capture of the same launch shape
+    # (profiles/r01_ncu_<kernel>.json, written by tools/ncu_summary.py); null when no capture of this shape exists.
+    traffic, traffic_src = None, None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_%s.json" % kname)))
+        if prof.get("batch") == Bl and prof.get("n_grid") == a.n_grid:
+            traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+            traffic_src = "profiles/r01_ncu_%s.json" % kname
+    except Exception:
+        pass
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
@@ -360,7 +376,7 @@ def run_ours(a):
         "gpu_launches": a.steps * (2 + 4 * rounds + 2 + 1),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "kernel": kname, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic, "traffic_source": traffic_src,
                      "kernel_ms": back_ms,
                      "note": "dominant kernel = backward Riccati sweep, one launch per step, timed alone with CUDA events; "
                              "achieved = executed useful fp64 flops of that launch (DESIGN.md flop model x the rhs / step / LU "
@@ -369,7 +385,7 @@ def run_ours(a):
                              "fp64-compute/latency bound, not HBM bound: see hbm_gbs" % nominal_tf,
                      "whole_step": {"achieved": fm["total"] / world / step_s / 1e12,
                                     "frac": (fm["total"] / world / step_s / 1e12 / peak_tf) if peak_tf else None},
-                     "hbm_gbs": {"achieved": None, "peak": mp.get("hbm_gbs")},
+                     "hbm_gbs": {"achieved": (traffic / (back_ms / 1e3) / 1e9) if traffic else None, "peak": mp.get("hbm_gbs")},
                      "flops_per_step": fm,
                      "phase_ms": {"solve": solve_ms, "aux_backward": back_ms, "aux_forward_loss_reduce": fwd_ms}},
         "stats": {"newton_iters_mean": loc[0] / B_total, "newton_rounds": rounds, "not_converged": int(loc[1]),

@@ -8,6 +8,7 @@
 //   CPDP_LAST_ERROR()                                           0 if no launch error
 #pragma once
 #include <cstddef>
+#include <cstdlib>
 #include <cstdint>
 
 namespace CPDP_NS {
@@ -53,7 +54,7 @@ static WsLayout ws_carve(char* base, int B, int N, int S) {
     a.act = takeI(B);
     a.nact = takeI(1);
     w.PW = takeD(BN1 * NYR);
-    w.Dbdf = takeD((size_t)B * 8 * NYR);      // differences arrays of k_riccati_bdf (BDF_NROWS = 8 rows per problem)
+    w.Dbdf = takeD((size_t)B * BDF_WS_ROWS * NYR);      // k_riccati_bdf: differences array + scale, psi, d rows per problem
     w.bytes = off;
     return w;
 }
@@ -161,7 +162,8 @@ static int cpdp_aux_impl(void* ws, size_t ws_bytes, int B, int N, int S, double 
             CPDP_PREPARE_SMEM(k_riccati_rk45, ric_bytes);
             CPDP_LAUNCH(k_riccati_rk45, B, AUX_THREADS, ric_bytes, st, a);
         } else {
-            const size_t bdf_bytes = BDF_SMEM_BYTES;
+            static const size_t bdf_pad = getenv("CPDP_BDF_SMEM_PAD") ? (size_t)atol(getenv("CPDP_BDF_SMEM_PAD")) : 0;   // tuning knob: CTAs per SM
+            const size_t bdf_bytes = BDF_SMEM_BYTES + bdf_pad;
             CPDP_PREPARE_SMEM(k_riccati_bdf, bdf_bytes);
             CPDP_LAUNCH(k_riccati_bdf, B, BDF_THREADS, bdf_bytes, st, a);
         }

@@ -32,10 +32,12 @@ constexpr int BDF_THREADS = 64;
 constexpr int BDF_MAX_ORDER = 5;
 constexpr int BDF_NEWTON_MAXITER = 4;
 constexpr int BDF_NROWS = BDF_MAX_ORDER + 3;
+constexpr int BDF_WS_ROWS = BDF_NROWS + 3;      // workspace rows per problem: differences array + scale, psi, d
 
 struct BdfShared {
     double* Tr; double* Ti;   // [NX*NX]  Schur form L = Z T Z^H (T upper triangular)
-    double* Zr; double* Zi;   // [NX*NX]
+    double* Zr;               // [NX*NX]  Q: REAL Schur vectors
+    double* ga; double* gbr; double* gbi; double* pi;   // [NX] each: block rotations G (Z = Q G^H), see bdf_schur
     double* Fr; double* Fi;   // [NX*NX]  scratch of the factor / solve steps
     double* Gr; double* Gi;   // [NX*NX]
     double* Dr; double* Di;   // [NT]     1 / ((1/2 + c t_ii) + conj(1/2 + c t_jj))
@@ -46,24 +48,26 @@ struct BdfShared {
     double* Rm;     // [NX*NX]  scratch: R                         (aliases Gr)
     double* D;      // [BDF_NROWS][NYR]  differences array, GLOBAL memory (L2-resident workspace): element (k, i) is
                     //                   only ever touched by the thread that owns column i (i % blockDim.x == tid)
-    double* ypred;  // [NYR]  predictor; between intervals it carries the interval's start / end state
-    double* scale; double* psi; double* d; double* y; double* dy;
-    double* RU;     // [6*6]
+    double* scale; double* psi; double* d;   // [NYR] each, GLOBAL memory (rows 8..10 of the workspace block), thread-private columns like D
+    double* y;      // [NYR]  Newton iterate (starts as the predictor); between intervals the interval's start / end state
+    double* dy;     // [NYR]
+    double* RU;     // [3][6*6]  change_D: RU, R, U
     double* Winv;   // [NX*NX]  inverse of I + c L
-    double* tmp;    // [NYR]    scratch of bdf_solve; f(t0, y0) during the start-up of an interval
+    double* tmp;    // [NYR]    scratch of bdf_solve (aliases Gr/Gi, dead by then) and of the start-up probe
     int* flag;      // [2]
 };
 
 CPDP_HD double bdf_kappa(int k) { const double v[6] = {0.0, -0.1850, -1.0 / 9, -0.0823, -0.0415, 0.0}; return v[k]; }
-CPDP_HD double bdf_gamma(int k) { double g = 0.0; for (int i = 1; i <= k; ++i) g += 1.0 / i; return g; }
+CPDP_HD constexpr double bdf_gamma(int k) { double g = 0.0; for (int i = 1; i <= k; ++i) g += 1.0 / i; return g; }
 CPDP_HD double bdf_alpha(int k) { return (1.0 - bdf_kappa(k)) * bdf_gamma(k); }
 CPDP_HD double bdf_error_const(int k) { return bdf_kappa(k) * bdf_gamma(k) + 1.0 / (k + 1); }
 
 // Shared-memory layout.  Every array sits at a COMPILE-TIME offset of the dynamic shared-memory block, so the
 // out-of-line pieces below rebuild their views from constants (no pointer structs in local memory, no registers).
-constexpr int BDF_SMEM_DOUBLES = MSZ + (2 * NX + NU) + (2 * BDF_THREADS + 2) + NX * NX + 2 * NU * NX + NU * NP   // AuxShared
-                                 + 8 * NX * NX + 2 * NT + NX * NP + NX * NX                                     // Schur data, Cm, Winv
-                                 + 6 * NYR + 36 + 8 + NYR + 2;                                                  // work vectors, RU, tms, tmp, flag
+constexpr int BDF_GSZ = (2 * NX * NX > NYR) ? 2 * NX * NX : NYR;      // (Gr, Gi) block; doubles as bdf_solve's NYR scratch
+constexpr int BDF_SMEM_DOUBLES = MSZ + (2 * NX + NU) + (BDF_THREADS + 2) + NX * NX + 2 * NU * NX + NU * NP       // AuxShared
+                                 + 5 * NX * NX + 4 * NX + BDF_GSZ + 2 * NT + NX * NP + NX * NX                           // Schur data, Cm, Winv
+                                 + 2 * NYR + 108 + 8 + 2;                                                        // y, dy, RU, tms, flag
 constexpr int BDF_SMEM_INTS = 2 * NT + SPTAB_INTS;
 constexpr size_t BDF_SMEM_BYTES = (size_t)BDF_SMEM_DOUBLES * sizeof(double) + (size_t)((BDF_SMEM_INTS + 3) & ~3) * sizeof(int);
 static_assert(NX * NU <= NX * NX, "GH aliases an NX x NX scratch matrix");
@@ -72,21 +76,22 @@ CPDP_D void bdf_layout(double* smem, AuxShared& s, BdfShared& bs, double*& tms) 
     double* ptr = smem;
     s.M = carve(ptr, MSZ);                       // one PMP slot: every Newton iterate of a step shares t_new
     s.xul = carve(ptr, 2 * NX + NU);
-    s.red = carve(ptr, 2 * BDF_THREADS + 2);
+    s.red = carve(ptr, BDF_THREADS + 2);
     s.P = carve(ptr, NX * NX);
     s.Y = carve(ptr, NU * NX);
     s.Yp = carve(ptr, NU * NX);
     s.Z = carve(ptr, NU * NP);
-    bs.Tr = carve(ptr, NX * NX); bs.Ti = carve(ptr, NX * NX); bs.Zr = carve(ptr, NX * NX); bs.Zi = carve(ptr, NX * NX);
-    bs.Fr = carve(ptr, NX * NX); bs.Fi = carve(ptr, NX * NX); bs.Gr = carve(ptr, NX * NX); bs.Gi = carve(ptr, NX * NX);
+    bs.Tr = carve(ptr, NX * NX); bs.Ti = carve(ptr, NX * NX); bs.Zr = carve(ptr, NX * NX);
+    bs.ga = carve(ptr, NX); bs.gbr = carve(ptr, NX); bs.gbi = carve(ptr, NX); bs.pi = carve(ptr, NX);
+    bs.Fr = carve(ptr, NX * NX); bs.Fi = carve(ptr, NX * NX); bs.Gr = carve(ptr, BDF_GSZ); bs.Gi = bs.Gr + NX * NX;
     bs.Dr = carve(ptr, NT); bs.Di = carve(ptr, NT);
     bs.Lm = bs.Fr; bs.Am = bs.Fi; bs.Rm = bs.Gr; bs.GH = bs.Gi;      // Jacobian scratch, dead once bdf_schur has copied Lm
     bs.Cm = carve(ptr, NX * NP); bs.Winv = carve(ptr, NX * NX);
-    bs.ypred = carve(ptr, NYR); bs.scale = carve(ptr, NYR); bs.psi = carve(ptr, NYR); bs.d = carve(ptr, NYR);
     bs.y = carve(ptr, NYR); bs.dy = carve(ptr, NYR);
-    bs.RU = carve(ptr, 36);
+    bs.RU = carve(ptr, 108);                     // RU | R | U, 6 x 6 each
     tms = carve(ptr, 8);
-    bs.tmp = carve(ptr, NYR);
+    bs.tmp = bs.Gr;
+    bs.scale = nullptr; bs.psi = nullptr; bs.d = nullptr;
     bs.flag = (int*)carve(ptr, 2);
     int* ip = (int*)(smem + BDF_SMEM_DOUBLES);
     s.ti = ip; s.tj = ip + NT;
@@ -94,6 +99,9 @@ CPDP_D void bdf_layout(double* smem, AuxShared& s, BdfShared& bs, double*& tms) 
     bs.D = nullptr;
 }
 #define BDF_LAYOUT() CPDP_DYN_SMEM(smem); AuxShared s; BdfShared bs; double* tms; bdf_layout(smem, s, bs, tms); (void)tms
+
+CPDP_D double bdf_reduce(double v, bool is_max) { BDF_LAYOUT(); return block_reduce(v, s.red, is_max); }
+CPDP_D double bdf_pow(double x, double y) { return pow(x, y); }
 
 // out-of-line instances of the shared right-hand side / PMP evaluation (one copy each instead of three)
 CPDP_D_NOINLINE void bdf_rhs(const double* yin, double* ydot) { BDF_LAYOUT(); riccati_rhs(s, s.M, yin, ydot); }
@@ -297,7 +305,7 @@ CPDP_D_NOINLINE bool bdf_schur() {
     constexpr int n = NX;
     const int tid = threadIdx.x, nt = blockDim.x;
     __syncthreads();
-    CPDP_LOOP for (int i = tid; i < n * n; i += nt) { bs.Tr[i] = bs.Lm[i]; bs.Ti[i] = 0.0; bs.Zi[i] = 0.0; }
+    CPDP_LOOP for (int i = tid; i < n * n; i += nt) { bs.Tr[i] = bs.Lm[i]; bs.Ti[i] = 0.0; }
     if (tid == 0) bs.flag[0] = 1;
     __syncthreads();
 #ifdef __CUDACC__
@@ -308,7 +316,11 @@ CPDP_D_NOINLINE bool bdf_schur() {
         const bool ok = schur_real_w0(bs.Tr, bs.Zr);
         CPDP_W0_SYNC();
         if (!ok && lane == 0) bs.flag[0] = 0;
-        // ---- one unitary rotation per 2 x 2 block:  G = [[c, s], [-conj(s), c]],  T <- G T G^H,  Z <- Z G^H
+        // ---- one unitary rotation per 2 x 2 block:  G = [[c, s], [-conj(s), c]],  T <- G T G^H.  The Schur vectors stay
+        //      REAL (Q = Zr); the block-diagonal unitary factor is kept as per-index coefficients (Z = Q G^H):
+        //      G[i][i] = ga[i] (real), G[i][pi[i]] = gb[i] (complex), pi[i] = the other index of i's block (or i).
+        if (lane < n) { bs.ga[lane] = 1.0; bs.gbr[lane] = 0.0; bs.gbi[lane] = 0.0; bs.pi[lane] = (double)lane; }
+        CPDP_W0_SYNC();
         CPDP_LOOP for (int j = 0; ok && j < n - 1; ++j) {
             const double cc = bs.Tr[(j + 1) * n + j];
             if (cc == 0.0) continue;
@@ -339,13 +351,9 @@ CPDP_D_NOINLINE bool bdf_schur() {
                 bs.Ti[k * n + j] = cr * xi + (sr * yi - si * yr);
                 bs.Tr[k * n + j + 1] = cr * yr - (sr * xr - si * xi);
                 bs.Ti[k * n + j + 1] = cr * yi - (sr * xi + si * xr);
-            } else if (lane >= 16 && lane < 16 + n) {                  // columns j, j+1 of Z
-                const int k = lane - 16;
-                const double xr = bs.Zr[k * n + j], xi = bs.Zi[k * n + j], yr = bs.Zr[k * n + j + 1], yi = bs.Zi[k * n + j + 1];
-                bs.Zr[k * n + j] = cr * xr + (sr * yr + si * yi);
-                bs.Zi[k * n + j] = cr * xi + (sr * yi - si * yr);
-                bs.Zr[k * n + j + 1] = cr * yr - (sr * xr - si * xi);
-                bs.Zi[k * n + j + 1] = cr * yi - (sr * xi + si * xr);
+            } else if (lane == 16) {
+                bs.ga[j] = cr; bs.gbr[j] = sr; bs.gbi[j] = si; bs.pi[j] = (double)(j + 1);
+                bs.ga[j + 1] = cr; bs.gbr[j + 1] = -sr; bs.gbi[j + 1] = si; bs.pi[j + 1] = (double)j;      // -conj(s)
             }
             CPDP_W0_SYNC();
             if (lane == 0) { bs.Tr[(j + 1) * n + j] = 0.0; bs.Ti[(j + 1) * n + j] = 0.0; }
@@ -354,6 +362,43 @@ CPDP_D_NOINLINE bool bdf_schur() {
     }
     __syncthreads();
     return bs.flag[0] != 0;
+}
+
+// Small dense products with three (two) outputs per thread in flight: the rolled 13-term dot products are latency
+// bound, independent accumulators overlap their shared-memory loads and DFMA chains without unrolling the loop.
+//   mm_nn:      out[i][k] = sum_j A[i][j] B[j][k]                       all n*n outputs
+//   mm_tri<TA>: v(i,j)    = sum_k (TA ? A[k][i] : A[i][k]) * (TA ? B[k][j] : B[j][k])   for the NT pairs i <= j
+CPDP_D void mm_nn(const double* A, const double* B, double* out) {
+    constexpr int n = NX;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    CPDP_LOOP for (int base = 0; base < n * n; base += 3 * nt) {
+        const int e0 = base + tid, e1 = e0 + nt, e2 = e1 + nt;
+        const int f0 = e0 < n * n ? e0 : 0, f1 = e1 < n * n ? e1 : 0, f2 = e2 < n * n ? e2 : 0;
+        const double* a0 = A + (f0 / n) * n; const double* a1 = A + (f1 / n) * n; const double* a2 = A + (f2 / n) * n;
+        const double* b0 = B + f0 % n; const double* b1 = B + f1 % n; const double* b2 = B + f2 % n;
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+        CPDP_LOOP for (int j = 0; j < n; ++j) { c0 += a0[j] * b0[j * n]; c1 += a1[j] * b1[j * n]; c2 += a2[j] * b2[j * n]; }
+        if (e0 < n * n) out[e0] = c0;
+        if (e1 < n * n) out[e1] = c1;
+        if (e2 < n * n) out[e2] = c2;
+    }
+}
+template <bool TA, class Store>
+CPDP_D void mm_tri(const AuxShared& s, const double* A, const double* B, Store store) {
+    constexpr int n = NX;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    CPDP_LOOP for (int base = 0; base < NT; base += 2 * nt) {
+        const int q0 = base + tid, q1 = q0 + nt;
+        const int r0 = q0 < NT ? q0 : 0, r1 = q1 < NT ? q1 : 0;
+        const int i0 = s.ti[r0], j0 = s.tj[r0], i1 = s.ti[r1], j1 = s.tj[r1];
+        const double* a0 = TA ? A + i0 : A + i0 * n; const double* b0 = TA ? B + j0 : B + j0 * n;
+        const double* a1 = TA ? A + i1 : A + i1 * n; const double* b1 = TA ? B + j1 : B + j1 * n;
+        constexpr int st = TA ? n : 1;
+        double c0 = 0.0, c1 = 0.0;
+        CPDP_LOOP for (int k = 0; k < n; ++k) { c0 += a0[k * st] * b0[k * st]; c1 += a1[k * st] * b1[k * st]; }
+        if (q0 < NT) store(q0, i0, j0, c0);
+        if (q1 < NT) store(q1, i1, j1, c1);
+    }
 }
 
 // scipy's "LU" event for a new c: reciprocals of the Lyapunov pivots and Winv = (I + c L)^{-1} = Re(Z (I + c T)^{-1} Z^H).
@@ -388,23 +433,37 @@ CPDP_D_NOINLINE bool bdf_factor(const double c) {
         if (!(dd > 0.0)) bad = 1.0;
         bs.Dr[q] = dr / dd; bs.Di[q] = -di / dd;
     }
-    bad = block_reduce(bad, s.red, true);
+    bad = bdf_reduce(bad, true);
     if (bad != 0.0) return false;
-    CPDP_LOOP for (int e = tid; e < n * n; e += nt) {          // G = Z S
-        const int i = e / n, k = e % n;
-        double gr = 0.0, gi = 0.0;
-        CPDP_LOOP for (int j = 0; j <= k; ++j) {
-            const double zr = bs.Zr[i * n + j], zi = bs.Zi[i * n + j], sr = bs.Fr[j * n + k], si = bs.Fi[j * n + k];
-            gr += zr * sr - zi * si;
-            gi += zr * si + zi * sr;
+    CPDP_LOOP for (int e = tid; e < n * n; e += nt) {          // Sr = Re(G^H S G) -> Gr   (real: (I + cL)^{-1} and Q are)
+        const int i = e / n, j = e % n;
+        const int pi = (int)bs.pi[i], pj = (int)bs.pi[j];
+        // conj(G[a][i]) for a in {i, pi}; G[b][j] for b in {j, pj}
+        const double ai_r = bs.ga[i], api_r = bs.gbr[pi], api_i = -bs.gbi[pi];
+        const double bj_r = bs.ga[j], bpj_r = bs.gbr[pj], bpj_i = bs.gbi[pj];
+        // t_b = conj(G[i][i]) S[i][b] + conj(G[pi][i]) S[pi][b]   for b = j and b = pj
+        double acc = 0.0;
+        {
+            const double s1r = bs.Fr[i * n + j], s1i = bs.Fi[i * n + j], s2r = bs.Fr[pi * n + j], s2i = bs.Fi[pi * n + j];
+            const double tr = ai_r * s1r + ((pi != i) ? (api_r * s2r - api_i * s2i) : 0.0);
+            const double ti = ai_r * s1i + ((pi != i) ? (api_r * s2i + api_i * s2r) : 0.0);
+            acc += tr * bj_r;  (void)ti;
         }
-        bs.Gr[e] = gr; bs.Gi[e] = gi;
+        if (pj != j) {
+            const double s1r = bs.Fr[i * n + pj], s1i = bs.Fi[i * n + pj], s2r = bs.Fr[pi * n + pj], s2i = bs.Fi[pi * n + pj];
+            const double tr = ai_r * s1r + ((pi != i) ? (api_r * s2r - api_i * s2i) : 0.0);
+            const double ti = ai_r * s1i + ((pi != i) ? (api_r * s2i + api_i * s2r) : 0.0);
+            acc += tr * bpj_r - ti * bpj_i;
+        }
+        bs.Gr[e] = acc;
     }
     __syncthreads();
-    CPDP_LOOP for (int e = tid; e < n * n; e += nt) {          // Winv = Re(G Z^H)
+    mm_nn(bs.Zr, bs.Gr, bs.Fr);                                // F = Q Sr
+    __syncthreads();
+    CPDP_LOOP for (int e = tid; e < n * n; e += nt) {          // Winv = F Q^T
         const int i = e / n, l = e % n;
         double acc = 0.0;
-        CPDP_LOOP for (int k = 0; k < n; ++k) acc += bs.Gr[i * n + k] * bs.Zr[l * n + k] + bs.Gi[i * n + k] * bs.Zi[l * n + k];
+        CPDP_LOOP for (int k = 0; k < n; ++k) acc += bs.Fr[i * n + k] * bs.Zr[l * n + k];
         bs.Winv[e] = acc;
     }
     __syncthreads();
@@ -418,25 +477,30 @@ CPDP_D_NOINLINE void bdf_solve(const double c) {
     constexpr int n = NX;
     const int tid = threadIdx.x, nt = blockDim.x;
     __syncthreads();
-    CPDP_LOOP for (int e = tid; e < n * n; e += nt) {          // F = B Z, B = sym(dy[0:NT])
-        const int i = e / n, k = e % n;
-        double fr = 0.0, fi = 0.0;
-        CPDP_LOOP for (int j = 0; j < n; ++j) {
-            const double b = dy[i <= j ? tri(i, j) : tri(j, i)];
-            fr += b * bs.Zr[j * n + k]; fi += b * bs.Zi[j * n + k];
-        }
-        bs.Fr[e] = fr; bs.Fi[e] = fi;
+    CPDP_LOOP for (int q = tid; q < NT; q += nt) {             // B = sym(dy[0:NT]) expanded -> P
+        const int i = s.ti[q], j = s.tj[q];
+        const double v = dy[q];
+        s.P[i * n + j] = v; s.P[j * n + i] = v;
     }
     __syncthreads();
-    CPDP_LOOP for (int q = tid; q < NT; q += nt) {             // C = Z^H F (upper triangle) -> (Gr, Gi)
+    mm_nn(s.P, bs.Zr, bs.Fr);                                  // F = B Q   (real)
+    __syncthreads();
+    {                                                          // Cr = Q^T F  (real symmetric, both triangles) -> Fi
+        double* Cr = bs.Fi;
+        mm_tri<true>(s, bs.Zr, bs.Fr, [Cr](int, int i, int j, double v) { Cr[i * n + j] = v; Cr[j * n + i] = v; });
+    }
+    __syncthreads();
+    CPDP_LOOP for (int q = tid; q < NT; q += nt) {             // C = G Cr G^H (upper triangle) -> (Gr, Gi)
         const int i = s.ti[q], j = s.tj[q];
-        double cr = 0.0, ci = 0.0;
-        CPDP_LOOP for (int k = 0; k < n; ++k) {
-            const double zr = bs.Zr[k * n + i], zi = bs.Zi[k * n + i], fr = bs.Fr[k * n + j], fi = bs.Fi[k * n + j];
-            cr += zr * fr + zi * fi;
-            ci += zr * fi - zi * fr;
-        }
-        bs.Gr[i * n + j] = cr; bs.Gi[i * n + j] = ci;
+        const int pi = (int)bs.pi[i], pj = (int)bs.pi[j];
+        const double gi_a = bs.ga[i], gi_br = bs.gbr[i], gi_bi = bs.gbi[i];       // G[i][i], G[i][pi]
+        const double gj_a = bs.ga[j], gj_br = bs.gbr[j], gj_bi = -bs.gbi[j];      // conj(G[j][j]), conj(G[j][pj])
+        // u_b = G[i][i] Cr[i][b] + G[i][pi] Cr[pi][b]    for b = j, pj
+        const double c1 = bs.Fi[i * n + j], c2 = bs.Fi[pi * n + j], c3 = bs.Fi[i * n + pj], c4 = bs.Fi[pi * n + pj];
+        const double ujr = gi_a * c1 + gi_br * c2, uji = gi_bi * c2;
+        const double upr = gi_a * c3 + gi_br * c4, upi = gi_bi * c4;
+        bs.Gr[i * n + j] = ujr * gj_a + (upr * gj_br - upi * gj_bi);
+        bs.Gi[i * n + j] = uji * gj_a + (upr * gj_bi + upi * gj_br);
     }
     __syncthreads();
     // ---- (1/2 + cT) Y + Y (1/2 + cT)^H = C along anti-diagonals i + j = d (warp 0; 4 lanes per entry); Y overwrites C,
@@ -451,17 +515,32 @@ CPDP_D_NOINLINE void bdf_solve(const double c) {
             const int i = ilo + e, j = d - i;
             const bool valid = (tid < 32) && (i <= j);
             double ar = 0.0, ai = 0.0;
-            if (valid) {
-                CPDP_LOOP for (int k = i + 1 + sub; k < n; k += 4) {           // T_ik Y_kj
-                    const double tr = bs.Tr[i * n + k], ti = bs.Ti[i * n + k], yr = bs.Gr[k * n + j], yi = bs.Gi[k * n + j];
-                    ar += tr * yr - ti * yi;
-                    ai += tr * yi + ti * yr;
+            {
+                // every lane issues the same unconditional (index-clamped) loads, out-of-range terms are zeroed by a
+                // select: no branches, all loads in flight together, one short DFMA chain per term
+                constexpr int M = (n + 2) / 4;
+                const int ic = valid ? i : 0, jc = valid ? j : 0;
+                double pr[2 * M], pi_[2 * M];
+#pragma unroll
+                for (int m = 0; m < M; ++m) {                                      // T_ik Y_kj,  k = i + 1 + sub + 4 m
+                    const int k = ic + 1 + sub + 4 * m;
+                    const bool in = valid && (k < n);
+                    const int kc = in ? k : 0;
+                    const double tr = bs.Tr[ic * n + kc], ti = bs.Ti[ic * n + kc], yr = bs.Gr[kc * n + jc], yi = bs.Gi[kc * n + jc];
+                    const double vr = tr * yr - ti * yi, vi = tr * yi + ti * yr;
+                    pr[m] = in ? vr : 0.0; pi_[m] = in ? vi : 0.0;
                 }
-                CPDP_LOOP for (int k = j + 1 + sub; k < n; k += 4) {           // Y_ik conj(T_jk)
-                    const double tr = bs.Tr[j * n + k], ti = bs.Ti[j * n + k], yr = bs.Gr[i * n + k], yi = bs.Gi[i * n + k];
-                    ar += yr * tr + yi * ti;
-                    ai += yi * tr - yr * ti;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {                                      // Y_ik conj(T_jk),  k = j + 1 + sub + 4 m
+                    const int k = jc + 1 + sub + 4 * m;
+                    const bool in = valid && (k < n);
+                    const int kc = in ? k : 0;
+                    const double tr = bs.Tr[jc * n + kc], ti = bs.Ti[jc * n + kc], yr = bs.Gr[ic * n + kc], yi = bs.Gi[ic * n + kc];
+                    const double vr = yr * tr + yi * ti, vi = yi * tr - yr * ti;
+                    pr[M + m] = in ? vr : 0.0; pi_[M + m] = in ? vi : 0.0;
                 }
+#pragma unroll
+                for (int m = 0; m < 2 * M; ++m) { ar += pr[m]; ai += pi_[m]; }
             }
 #ifdef __CUDACC__
             ar += __shfl_xor_sync(0xffffffffu, ar, 1); ai += __shfl_xor_sync(0xffffffffu, ai, 1);
@@ -486,29 +565,31 @@ CPDP_D_NOINLINE void bdf_solve(const double c) {
         }
     }
     __syncthreads();
-    CPDP_LOOP for (int e = tid; e < n * n; e += nt) {          // F = Z Y
-        const int i = e / n, k = e % n;
-        double fr = 0.0, fi = 0.0;
-        CPDP_LOOP for (int j = 0; j < n; ++j) {
-            const double zr = bs.Zr[i * n + j], zi = bs.Zi[i * n + j], yr = bs.Gr[j * n + k], yi = bs.Gi[j * n + k];
-            fr += zr * yr - zi * yi;
-            fi += zr * yi + zi * yr;
-        }
-        bs.Fr[e] = fr; bs.Fi[e] = fi;
+    CPDP_LOOP for (int q = tid; q < NT; q += nt) {             // Yr = Re(G^H Y G)  (real symmetric, both triangles) -> Fr
+        const int i = s.ti[q], j = s.tj[q];
+        const int pi = (int)bs.pi[i], pj = (int)bs.pi[j];
+        const double ai_r = bs.ga[i], ap_r = bs.gbr[pi], ap_i = -bs.gbi[pi];      // conj(G[i][i]), conj(G[pi][i])
+        const double bj_r = bs.ga[j], bp_r = bs.gbr[pj], bp_i = bs.gbi[pj];       // G[j][j], G[pj][j]
+        const double y1r = bs.Gr[i * n + j], y1i = bs.Gi[i * n + j], y2r = bs.Gr[pi * n + j], y2i = bs.Gi[pi * n + j];
+        const double y3r = bs.Gr[i * n + pj], y3i = bs.Gi[i * n + pj], y4r = bs.Gr[pi * n + pj], y4i = bs.Gi[pi * n + pj];
+        const double tjr = ai_r * y1r + (ap_r * y2r - ap_i * y2i);
+        const double tpr = ai_r * y3r + (ap_r * y4r - ap_i * y4i), tpi = ai_r * y3i + (ap_r * y4i + ap_i * y4r);
+        const double v = tjr * bj_r + (tpr * bp_r - tpi * bp_i);
+        bs.Fr[i * n + j] = v; bs.Fr[j * n + i] = v;
     }
     __syncthreads();
-    CPDP_LOOP for (int q = tid; q < NT; q += nt) {             // X = Re(F Z^H), upper triangle
-        const int i = s.ti[q], l = s.tj[q];
-        double acc = 0.0;
-        CPDP_LOOP for (int k = 0; k < n; ++k) acc += bs.Fr[i * n + k] * bs.Zr[l * n + k] + bs.Fi[i * n + k] * bs.Zi[l * n + k];
-        tmp[q] = acc;
+    mm_nn(bs.Zr, bs.Fr, bs.Fi);                                // F2 = Q Yr -> Fi
+    __syncthreads();
+    {                                                          // X = F2 Q^T, upper triangle -> tmp and expanded -> P
+        double* Pm = s.P;
+        mm_tri<false>(s, bs.Fi, bs.Zr, [tmp, Pm](int q, int i, int l, double v) { tmp[q] = v; Pm[i * n + l] = v; Pm[l * n + i] = v; });
     }
     __syncthreads();
     double* dW = dy + NT;
     CPDP_LOOP for (int e = tid; e < NX * NP; e += nt) {                  // B_W + c X C
         const int i = e / NP, k = e % NP;
         double acc = 0.0;
-        CPDP_LOOP for (int a = 0; a < NX; ++a) acc += tmp[i <= a ? tri(i, a) : tri(a, i)] * bs.Cm[a * NP + k];
+        CPDP_LOOP for (int a = 0; a < NX; ++a) acc += s.P[i * NX + a] * bs.Cm[a * NP + k];
         tmp[NT + e] = dW[e] + c * acc;
     }
     CPDP_LOOP for (int k = tid; k < NT; k += nt) dy[k] = tmp[k];
@@ -527,34 +608,39 @@ CPDP_D_NOINLINE void bdf_change_D(double* D, const int order, const double facto
     BDF_LAYOUT();
     bs.D = D;
     const int tid = threadIdx.x, nt = blockDim.x;
+    double* R = bs.RU + 36; double* U = bs.RU + 72;         // 6 x 6 scratch
     __syncthreads();
-    if (tid == 0) {
-        double R[6][6], U[6][6];
-        CPDP_LOOP for (int j = 0; j <= order; ++j) { R[0][j] = 1.0; U[0][j] = 1.0; }
+    if (tid <= order) {                                     // column tid of R and U: cumprod down the rows (compute_R)
+        const int j = tid;
+        R[j] = 1.0; U[j] = 1.0;
         CPDP_LOOP for (int i = 1; i <= order; ++i) {
-            R[i][0] = 0.0; U[i][0] = 0.0;
-            CPDP_LOOP for (int j = 1; j <= order; ++j) {
-                R[i][j] = R[i - 1][j] * (((double)(i - 1) - factor * j) / i);
-                U[i][j] = U[i - 1][j] * (((double)(i - 1) - (double)j) / i);
-            }
+            R[i * 6 + j] = (j == 0) ? 0.0 : R[(i - 1) * 6 + j] * (((double)(i - 1) - factor * j) / i);
+            U[i * 6 + j] = (j == 0) ? 0.0 : U[(i - 1) * 6 + j] * (((double)(i - 1) - (double)j) / i);
         }
-        CPDP_LOOP for (int i = 0; i <= order; ++i)
-            CPDP_LOOP for (int j = 0; j <= order; ++j) {
-                double acc = 0.0;
-                CPDP_LOOP for (int k = 0; k <= order; ++k) acc += R[i][k] * U[k][j];
-                bs.RU[i * 6 + j] = acc;
-            }
+    }
+    __syncthreads();
+    if (tid < 36) {
+        const int i = tid / 6, j = tid % 6;
+        if (i <= order && j <= order) {
+            double acc = 0.0;
+            CPDP_LOOP for (int k = 0; k <= order; ++k) acc += R[i * 6 + k] * U[k * 6 + j];
+            bs.RU[i * 6 + j] = acc;
+        }
     }
     __syncthreads();
     CPDP_LOOP for (int q = tid; q < NYR; q += nt) {
-        double v[6], o[6];
-        CPDP_LOOP for (int i = 0; i <= order; ++i) v[i] = bs.D[(size_t)i * NYR + q];
-        CPDP_LOOP for (int i = 0; i <= order; ++i) {
-            double acc = 0.0;
-            CPDP_LOOP for (int j = 0; j <= order; ++j) acc += bs.RU[j * 6 + i] * v[j];
-            o[i] = acc;
+        double v[BDF_MAX_ORDER + 1];
+#pragma unroll
+        for (int i = 0; i <= BDF_MAX_ORDER; ++i) v[i] = (i <= order) ? bs.D[(size_t)i * NYR + q] : 0.0;
+#pragma unroll
+        for (int i = 0; i <= BDF_MAX_ORDER; ++i) {
+            if (i <= order) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j <= BDF_MAX_ORDER; ++j) if (j <= order) acc += bs.RU[j * 6 + i] * v[j];
+                bs.D[(size_t)i * NYR + q] = acc;
+            }
         }
-        CPDP_LOOP for (int i = 0; i <= order; ++i) bs.D[(size_t)i * NYR + q] = o[i];
     }
     __syncthreads();
 }
@@ -565,7 +651,7 @@ CPDP_D_NOINLINE double bdf_norm(const double* v, const double* scale, const doub
     const int tid = threadIdx.x, nt = blockDim.x;
     double a = 0.0;
     CPDP_LOOP for (int i = tid; i < NYR; i += nt) { const double x = mul * v[i] / scale[i]; a += ric_wgt(s, i) * x * x; }
-    return sqrt(block_reduce(a, s.red, false) / (double)NFULL_R);
+    return sqrt(bdf_reduce(a, false) / (double)NFULL_R);
 }
 
 // One grid interval [t0, t1] with scipy's BDF.  y in/out (shared memory).  Returns 0 ok, 1 step too small,
@@ -578,7 +664,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
     // ---- __init__ (bdf.py:200-257)
     if (tid == 0) tms[0] = t0;
     if (!bdf_prepare(p)) return 2;
-    double* f0 = bs.tmp;               // f(t0, y0): bdf_solve (the other user of tmp) is not called during start-up
+    double* f0 = bs.d;                 // f(t0, y0) parked in the (not yet used) d row
     bdf_rhs(y, f0); ++cnt[0];
     bdf_jacobian(y); ++cnt[3];
     if (!bdf_schur()) return 4;
@@ -591,24 +677,24 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
             a0 += ric_wgt(s, i) * (y[i] / sc) * (y[i] / sc);
             a1 += ric_wgt(s, i) * (f0[i] / sc) * (f0[i] / sc);
         }
-        const double d0 = sqrt(block_reduce(a0, s.red, false) / (double)NFULL_R);
-        const double d1 = sqrt(block_reduce(a1, s.red, false) / (double)NFULL_R);
+        const double d0 = sqrt(bdf_reduce(a0, false) / (double)NFULL_R);
+        const double d1 = sqrt(bdf_reduce(a1, false) / (double)NFULL_R);
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         h0 = fmin(h0, interval_length);
-        CPDP_LOOP for (int i = tid; i < NYR; i += nt) bs.y[i] = y[i] + h0 * dir * f0[i];
+        CPDP_LOOP for (int i = tid; i < NYR; i += nt) bs.dy[i] = y[i] + h0 * dir * f0[i];
         if (tid == 0) tms[0] = t0 + h0 * dir;
         if (!bdf_prepare(p)) return 2;
-        bdf_rhs(bs.y, bs.dy); ++cnt[0];
+        bdf_rhs(bs.dy, bs.tmp); ++cnt[0];
         double a2 = 0.0;
         CPDP_LOOP for (int i = tid; i < NYR; i += nt) {
             const double sc = atol + fabs(y[i]) * rtol;
-            const double v = (bs.dy[i] - f0[i]) / sc;
+            const double v = (bs.tmp[i] - f0[i]) / sc;
             a2 += ric_wgt(s, i) * v * v;
         }
-        const double d2 = sqrt(block_reduce(a2, s.red, false) / (double)NFULL_R) / h0;
+        const double d2 = sqrt(bdf_reduce(a2, false) / (double)NFULL_R) / h0;
         double h1;
         if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
-        else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 2.0);       // order 1
+        else h1 = bdf_pow(0.01 / fmax(d1, d2), 1.0 / 2.0);       // order 1
         h_abs = fmin(fmin(100 * h0, h1), interval_length);
     }
     const double newton_tol = fmax(10 * EPS / rtol, fmin(0.03, sqrt(rtol)));
@@ -642,14 +728,18 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
             }
             h = t_new - t;
             h_abs = fabs(h);
-            double gam[6];
-            CPDP_LOOP for (int k = 1; k <= order; ++k) gam[k] = bdf_gamma(k);
             const double al = bdf_alpha(order);
             CPDP_LOOP for (int i = tid; i < NYR; i += nt) {
                 double yp = 0.0, ps = 0.0;
-                CPDP_LOOP for (int k = 0; k <= order; ++k) yp += bs.D[(size_t)k * NYR + i];
-                CPDP_LOOP for (int k = 1; k <= order; ++k) ps += bs.D[(size_t)k * NYR + i] * gam[k];
-                bs.ypred[i] = yp;
+#pragma unroll
+                for (int k = 0; k <= BDF_MAX_ORDER; ++k) {
+                    if (k <= order) {
+                        const double v = bs.D[(size_t)k * NYR + i];
+                        yp += v;
+                        if (k >= 1) ps += v * bdf_gamma(k);
+                    }
+                }
+                bs.y[i] = yp;                                     // y_predict: the Newton iteration starts from it
                 bs.scale[i] = atol + rtol * fabs(yp);
                 bs.psi[i] = ps / al;
             }
@@ -663,7 +753,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                     lu_valid = true; c_lu = c; ++cnt[2];
                 }
                 // ---- solve_bdf_system (bdf.py:36-75)
-                CPDP_LOOP for (int i = tid; i < NYR; i += nt) { bs.d[i] = 0.0; bs.y[i] = bs.ypred[i]; }
+                CPDP_LOOP for (int i = tid; i < NYR; i += nt) bs.d[i] = 0.0;
                 __syncthreads();
                 double dy_norm_old = -1.0;
                 int k = 0;
@@ -675,13 +765,13 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                         if (!(fabs(fv) < 1e300)) fin = 1.0;
                         bs.dy[i] = c * fv - bs.psi[i] - bs.d[i];
                     }
-                    fin = block_reduce(fin, s.red, true);
+                    fin = bdf_reduce(fin, true);
                     if (fin != 0.0) break;
                     bdf_solve(c_lu);
                     const double dy_norm = bdf_norm(bs.dy, bs.scale, 1.0);
                     const bool have_rate = dy_norm_old >= 0.0;
                     const double rate = have_rate ? dy_norm / dy_norm_old : 0.0;
-                    if (have_rate && (rate >= 1 || pow(rate, (double)(BDF_NEWTON_MAXITER - k)) / (1 - rate) * dy_norm > newton_tol)) break;
+                    if (have_rate && (rate >= 1 || bdf_pow(rate, (double)(BDF_NEWTON_MAXITER - k)) / (1 - rate) * dy_norm > newton_tol)) break;
                     CPDP_LOOP for (int i = tid; i < NYR; i += nt) { bs.y[i] += bs.dy[i]; bs.d[i] += bs.dy[i]; }
                     __syncthreads();
                     if (dy_norm == 0 || (have_rate && rate / (1 - rate) * dy_norm < newton_tol)) { converged = true; break; }
@@ -690,7 +780,13 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                 n_iter = (k < BDF_NEWTON_MAXITER) ? k + 1 : BDF_NEWTON_MAXITER;
                 if (!converged) {
                     if (current_jac) break;
-                    bdf_jacobian(bs.ypred); ++cnt[3];
+                    // back to y_predict (same sum, same order => same bits as above), Jacobian there (bdf.py:372)
+                    CPDP_LOOP for (int i = tid; i < NYR; i += nt) {
+                        double yp = 0.0;
+                        CPDP_LOOP for (int k = 0; k <= order; ++k) yp += bs.D[(size_t)k * NYR + i];
+                        bs.y[i] = yp;
+                    }
+                    bdf_jacobian(bs.y); ++cnt[3];
                     if (!bdf_schur()) return 4;
                     lu_valid = false;
                     current_jac = true;
@@ -709,7 +805,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
             error_norm = bdf_norm(bs.d, bs.scale, bdf_error_const(order));
             if (!(error_norm == error_norm)) return 2;
             if (error_norm > 1) {
-                const double factor = fmax(0.2, safety * pow(error_norm, -1.0 / (order + 1)));
+                const double factor = fmax(0.2, safety * bdf_pow(error_norm, -1.0 / (order + 1)));
                 h_abs *= factor;
                 bdf_change_D(bs.D, order, factor);
                 n_equal_steps = 0;
@@ -733,9 +829,9 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
         double error_m_norm = INFINITY, error_p_norm = INFINITY;
         if (order > 1) error_m_norm = bdf_norm(bs.D + (size_t)order * NYR, bs.scale, bdf_error_const(order - 1));
         if (order < BDF_MAX_ORDER) error_p_norm = bdf_norm(bs.D + (size_t)(order + 2) * NYR, bs.scale, bdf_error_const(order + 1));
-        const double fm = pow(error_m_norm, -1.0 / order);
-        const double f0 = pow(error_norm, -1.0 / (order + 1));
-        const double fp = pow(error_p_norm, -1.0 / (order + 2));
+        const double fm = bdf_pow(error_m_norm, -1.0 / order);
+        const double f0 = bdf_pow(error_norm, -1.0 / (order + 1));
+        const double fp = bdf_pow(error_p_norm, -1.0 / (order + 2));
         int delta_order = -1; double fmaxv = fm;          // np.argmax: first maximum
         if (f0 > fmaxv) { fmaxv = f0; delta_order = 0; }
         if (fp > fmaxv) { fmaxv = fp; delta_order = 1; }
@@ -753,7 +849,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
 }
 
 // k_riccati_bdf: backward sweep of COCSys.auxSysSolver as shipped (CPDP.py:327-338).
-CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, 6) k_riccati_bdf(AuxArgs a) {
+CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, 7) k_riccati_bdf(AuxArgs a) {
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     if (a.solve_status && (a.solve_status[b] == ST_NUMERIC || a.solve_status[b] == ST_RUNNING)) {
         if (tid == 0) a.aux_status[b] = 3;
@@ -770,8 +866,9 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, 6) k_riccati_bdf(AuxArgs a) {
     }
     CPDP_LOOP for (int q = tid; q < MSZ; q += nt) s.M[q] = 0.0;
     aux_tables(s, (int*)s.ti + 2 * NT);
-    bs.D = a.Dws + (size_t)b * BDF_NROWS * NYR;
-    double* y = bs.ypred;                        // state at the interval boundaries (the predictor is dead there)
+    bs.D = a.Dws + (size_t)b * BDF_WS_ROWS * NYR;
+    bs.scale = bs.D + (size_t)BDF_NROWS * NYR; bs.psi = bs.scale + NYR; bs.d = bs.psi + NYR;
+    double* y = bs.y;                            // state at the interval boundaries
     const int N = a.N;
     AuxProblem p;
     p.X = a.X + (size_t)b * (N + 1) * NX; p.U = a.U + (size_t)b * (N + 1) * NU; p.Lam = a.Lam + (size_t)b * (N + 1) * NX;

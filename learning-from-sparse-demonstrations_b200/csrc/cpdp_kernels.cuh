@@ -106,7 +106,10 @@ CPDP_HD void rk4_interval(const double* x, const double* u, const double* th, co
 // ------------------------------------------------------------------------------------------------
 CPDP_D void stage_adjoint_item(const SolveArgs& a, int b, int k);
 
-CPDP_GLOBAL void __launch_bounds__(128) k_stage_adjoint(SolveArgs a) {
+#ifndef CPDP_ADJ_MINB
+#define CPDP_ADJ_MINB 1
+#endif
+CPDP_GLOBAL void __launch_bounds__(128, CPDP_ADJ_MINB) k_stage_adjoint(SolveArgs a) {
     const int total = *a.nact * a.N;
     for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x)
         stage_adjoint_item(a, a.act[item / a.N], item % a.N);
@@ -191,7 +194,10 @@ CPDP_D void stage_adjoint_item(const SolveArgs& a, int b, int k) {
 constexpr int HESS_THREADS = 256;
 constexpr int KPC = HESS_THREADS / NZ;          // intervals per CTA
 
-CPDP_GLOBAL void __launch_bounds__(HESS_THREADS) k_stage_hessian(SolveArgs a) {
+#ifndef CPDP_HESS_MINB
+#define CPDP_HESS_MINB 1
+#endif
+CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian(SolveArgs a) {
     CPDP_SHARED double s_x[KPC][NX];
     CPDP_SHARED double s_mu[KPC][NX];
     CPDP_SHARED double s_u[KPC][NU];
@@ -631,7 +637,10 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
     if (tid == 0) a.iters[b] = it + 1;
 }
 
-CPDP_GLOBAL void __launch_bounds__(NEWTON_THREADS) k_newton_step(SolveArgs a) {
+#ifndef CPDP_NEWTON_MINB
+#define CPDP_NEWTON_MINB 1
+#endif
+CPDP_GLOBAL void __launch_bounds__(NEWTON_THREADS, CPDP_NEWTON_MINB) k_newton_step(SolveArgs a) {
     const int nact = *a.nact;
     for (int pi = blockIdx.x; pi < nact; pi += gridDim.x) {
         newton_step_problem(a, a.act[pi]);

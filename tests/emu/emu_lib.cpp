@@ -71,7 +71,7 @@ void k_emu_bdf_linear(const double* L, const double* Cm, double c, const double*
     if (good) bdf_solve(c);
     __syncthreads();
     for (int i = tid; i < NX * NX; i += nt) {
-        out_TZ[i] = bs.Tr[i]; out_TZ[NX * NX + i] = bs.Ti[i]; out_TZ[2 * NX * NX + i] = bs.Zr[i]; out_TZ[3 * NX * NX + i] = bs.Zi[i];
+        out_TZ[i] = bs.Tr[i]; out_TZ[NX * NX + i] = bs.Ti[i]; out_TZ[2 * NX * NX + i] = bs.Zr[i]; out_TZ[3 * NX * NX + i] = (i < 4 * NX) ? bs.ga[i] : 0.0;   // ga | gbr | gbi | pi (contiguous)
         out_TZ[4 * NX * NX + i] = bs.Winv[i];
     }
     for (int i = tid; i < NYR; i += nt) out_sol[i] = bs.dy[i];

@@ -20,13 +20,17 @@ def main():
     ap.add_argument("--mode", default="bdf")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--phases", type=int, default=1)
+    ap.add_argument("--name", default=None, help="library name (variants built under other names)")
+    ap.add_argument("--build-only", action="store_true")
     a = ap.parse_args()
-    import torch
     import lfsd_b200  # noqa: F401
     from lfsd_b200 import standard, synthetic
     oc = standard.quadrotor_oc(n_grid=a.n_grid)
-    oc.build(name=oc.lib_name)
+    oc.build(name=a.name or oc.lib_name)
+    if a.build_only:
+        return
     oc.aux_mode = oc.MODE_BDF if a.mode == "bdf" else oc.MODE_RK45
+    import torch
     qb = synthetic.quad_batch(a.batch)
     sol = oc.cocSolverBatch(qb["x0"], 1.0, qb["theta"], pdata=qb["goal"])
     torch.cuda.synchronize()
