@@ -82,8 +82,14 @@ def cpu_baseline(n_grid, sample, steps=1, warmup=0, max_workers=0, deadline_s=24
     """Oracle (the CPU restatement of the reference algorithm) on a bounded sample of the same synthetic batch, one
     process per host core.  Each step maps `sample` OCPs (default: four per worker) over the pool; the run stops
     taking new steps after `deadline_s`.  Returns (cpu_baseline dict, seconds, steps done)."""
-    from multiprocessing import Pool
+    import multiprocessing
     from lfsd_b200 import synthetic
+    # one BLAS / OpenMP thread per worker, decided before the workers import numpy: fresh interpreters (spawn) that inherit
+    # these variables.  (Forked workers inherit an already initialised all-core BLAS pool; threadpoolctl alone did not
+    # tame it when torch had not been imported first, and 16 x 16 spinning threads never finish.)
+    for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[var] = "1"
+    Pool = multiprocessing.get_context("spawn").Pool
     cores = os.cpu_count() or 1
     workers = min(cores, max_workers) if max_workers else cores
     sample = sample or 4 * workers          # ~10-15 s of CPU work on the box's cores
