@@ -214,3 +214,29 @@ def test_full_size_properties(torch_mod):
     fx = _fx("quad50")
     nb = fx["X"].shape[0]
     assert _rel(X[:nb], fx["X"]) < TRAJ_RTOL          # first problems of the batch are the oracle fixture
+
+
+def test_stored_run_learning_trace(torch_mod):
+    """The reference's own stored run, replayed end to end through the CUDA path: 20 Nesterov iterations (learner of
+    /root/reference/lib/QuadAlgorithm.py:239-257,469-494 in lfsd_b200.optim, every loss / gradient from
+    cocSolver + auxSysSolver(BDF) + loss on the GPU) against parameter_trace / loss_trace of
+    data/uav_results_random_20210308113016.mat.  Each gradient is within ~2e-7 of the reference's, the recurrence
+    accumulates it; tolerance 1e-5 relative on theta_j and 1e-6 on the losses."""
+    from lfsd_b200.optim import Learner, cpdp_grad_fn
+    g = np.load(os.path.join(HERE, "golden", "quad_run.npz"))
+    oc = _oc("quadrotor", 25)
+    if not _has_bdf(oc):
+        pytest.skip("library built without the BDF sweep")
+    oc.aux_mode = oc.MODE_BDF
+    oc.rtol_back, oc.atol_back, oc.rtol_fwd, oc.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
+    P, lr, mu = g["parameter_trace"], float(g["learning_rate"]), float(g["mu"])
+    fn = cpdp_grad_fn(oc, g["ini_state"].reshape(1, 13), 1.0, g["time_grid"], g["waypoints"].reshape(1, -1, 3), [0, 1, 2],
+                      pdata=g["goal_position"].reshape(1, 3))
+    L = Learner(fn, 7)
+    L.load_optimization_function({"learning_rate": lr, "iter_num": 20, "method": "Nesterov", "mu": mu, "true_loss_print_flag": False})
+    L.run(P[0])
+    got = np.array(L.parameter_trace)
+    assert got.shape == (21, 7)
+    for j in range(21):
+        assert _rel(got[j], P[j]) < GRAD_RTOL, (j, got[j], P[j])
+    assert np.allclose(L.loss_trace, g["loss_trace"][:20], rtol=1e-6)
