@@ -519,6 +519,7 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
         ++attempt;
         if (delta > 1e40) {
             if (tid == 0) a.status[b] = ST_NUMERIC;
+            for (int i = tid; i < NU; i += nt) U[(size_t)N * NU + i] = U[(size_t)(N - 1) * NU + i];   // CPDP.py:191 holds whatever the solver returned
             return;
         }
         __syncthreads();
@@ -571,7 +572,11 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
     for (int i = tid; i < NX; i += nt) gd += s_hx[i] * dX[(size_t)N * NX + i];
     bad = block_reduce(bad, red, true);
     gd = block_reduce(gd, red, false);
-    if (bad != 0.0 || !(gd == gd)) { if (tid == 0) a.status[b] = ST_NUMERIC; return; }
+    if (bad != 0.0 || !(gd == gd)) {
+        if (tid == 0) a.status[b] = ST_NUMERIC;
+        for (int i = tid; i < NU; i += nt) U[(size_t)N * NU + i] = U[(size_t)(N - 1) * NU + i];
+        return;
+    }
 
     // ---- IPOPT filter line search (Waechter & Biegler 2006, Sec. 2.3; phi = J, theta = |g|_1, default constants
     //      gamma_theta 1e-5, gamma_phi 1e-8, delta 1, s_theta 1.1, s_phi 2.3, eta_phi 1e-8; no second-order
@@ -621,7 +626,11 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
         if (acc) { ok = true; break; }
         alpha *= 0.5;
     }
-    if (!ok) { if (tid == 0) a.status[b] = ST_LINESEARCH; return; }
+    if (!ok) {
+        if (tid == 0) a.status[b] = ST_LINESEARCH;
+        for (int i = tid; i < NU; i += nt) U[(size_t)N * NU + i] = U[(size_t)(N - 1) * NU + i];
+        return;
+    }
     if (!ftype && tid == 0 && nf < FILTER_CAP) {
         a.filt[((size_t)b * FILTER_CAP + nf) * 2] = (1 - 1e-5) * th0;
         a.filt[((size_t)b * FILTER_CAP + nf) * 2 + 1] = J0 - 1e-8 * th0;
