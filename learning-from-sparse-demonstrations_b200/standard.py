@@ -45,6 +45,17 @@ def robotarm_oc(n_grid=30):
     return oc
 
 
+def cartpole_oc(n_grid=20):
+    """JinEnv.CartPole (JinEnv.py:499-574) behind the same time-warping wrapper; no example script of the reference uses
+    it, constants as in the upstream PDP examples (mc = mp = 0.5, l = 1, wu = 0.1); observed: x, q."""
+    env = JinEnv.CartPole()
+    env.initDyn(mc=0.5, mp=0.5, l=1)
+    env.initCost(wu=0.1)
+    oc = _wrap(env, "cartpole", n_grid)
+    oc.sel = [0, 1]
+    return oc
+
+
 def rocket_oc(n_grid=15):
     """Examples/rocket_groundtruth.py:15-30 ; observed: position and quaternion."""
     env = JinEnv.Rocket()
@@ -78,7 +89,8 @@ def quadrotor_oc(n_grid=25, goal_position=None):
     return oc
 
 
-STANDARD = {"pendulum": pendulum_oc, "robotarm": robotarm_oc, "rocket": rocket_oc, "quadrotor": quadrotor_oc}
+STANDARD = {"pendulum": pendulum_oc, "robotarm": robotarm_oc, "rocket": rocket_oc, "quadrotor": quadrotor_oc,
+            "cartpole": cartpole_oc}
 
 
 def build_all(verbose=False):

@@ -10,6 +10,7 @@ Follows:
   * RobotArm        /root/reference/JinEnv/JinEnv.py:183-237, 287-326
   * Quadrotor       /root/reference/JinEnv/JinEnv.py:680-753, 886-953, 1182-1205
   * Rocket          /root/reference/JinEnv/JinEnv.py:1266-1326, 1401-1473
+  * CartPole        /root/reference/JinEnv/JinEnv.py:504-574
   * beta wrapper    /root/reference/Examples/pendulum_groundtruth.py:21-30 (same in every example,
                     /root/reference/lib/QuadAlgorithm.py:89-98)
 """
@@ -136,6 +137,21 @@ def rocket(J=(1.0, 1.0, 1.0), mass=1.0, l=1.0, wthrust=0.1):
     c = h + wside * (u[1] ** 2 + u[2] ** 2) + wthrust * sum(ui ** 2 for ui in u)
     return OracleModel('rocket', r + v + q + w, u, [beta] + wts, beta * f, beta * c, h,
                        sel=[0, 1, 2, 6, 7, 8, 9])
+
+
+def cartpole(mc=0.5, mp=0.5, l=1.0, wu=0.1):
+    """JinEnv.py:504-574 with numeric mc, mp, l; weights [wx, wq, wdx, wdq] learnable; goal [0, pi, 0, 0]; g = 10."""
+    x, q, dx, dq = _syms('x q dx dq')
+    u, = _syms('u')
+    beta, wx, wq, wdx, wdq = _syms('beta wx wq wdx wdq')
+    g = 10
+    ddx = (u + mp * sp.sin(q) * (l * dq * dq + g * sp.cos(q))) / (mc + mp * sp.sin(q) * sp.sin(q))
+    ddq = (-u * sp.cos(q) - mp * l * dq * dq * sp.sin(q) * sp.cos(q) - (mc + mp) * g * sp.sin(q)) / \
+        (l * mc + l * mp * sp.sin(q) * sp.sin(q))
+    f = sp.Matrix([dx, dq, ddx, ddq])
+    h = wx * (x - 0.0) ** 2 + wq * (q - math.pi) ** 2 + wdx * (dx - 0.0) ** 2 + wdq * (dq - 0.0) ** 2
+    c = h + wu * (u * u)
+    return OracleModel('cartpole', [x, q, dx, dq], [u], [beta, wx, wq, wdx, wdq], beta * f, beta * c, h, sel=[0, 1])
 
 
 def to_quaternion(angle, axis):

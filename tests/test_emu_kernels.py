@@ -159,3 +159,27 @@ def test_quad_k4_gradient_bdf_vs_stored_run(quad):
     assert int(aux["aux_status"][0]) == 0
     assert abs(aux["loss"][0] - g["loss_trace"][0]) / g["loss_trace"][0] < 1e-8
     assert _rel(aux["dtheta"][0], (P[0] - P[1]) / lr) < 1e-5
+
+
+def test_cartpole_through_codegen_vs_oracle():
+    """a JinEnv definition no example script uses (CartPole) goes through the same code generation and
+    kernels; checked against the oracle's independent restatement of the model."""
+    cp = emu_oc("cartpole")
+    orc = Oracle(models.cartpole(), n_grid=20)
+    th = np.array([1.5, 0.5, 1.0, 0.2, 0.3])
+    x0 = np.array([0.0, 0.3, 0.0, 0.0])
+    sol = cp.cocSolverBatch(x0.reshape(1, 4), 1.0, th)
+    tg, X, U, Lam, info = orc.solve(x0, 1.0, th, return_info=True)
+    assert int(sol["status"][0]) == 1 and int(sol["iters"][0]) == info["iters"]
+    assert np.abs(sol["X"][0] - X).max() < 1e-8 * max(1.0, np.abs(X).max())
+    assert np.abs(sol["Lam"][0] - Lam).max() < 1e-7 * max(1.0, np.abs(Lam).max())
+    taus, wp = np.array([0.25, 0.7]), np.array([[[0.1, 1.0], [0.0, 2.5]]])
+    for mode, back in ((cp.MODE_RK45, {}), (cp.MODE_BDF, {'method': 'BDF', 'jac': 'closed'})):
+        cp.aux_mode = mode
+        cp.rtol_back, cp.atol_back, cp.rtol_fwd, cp.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
+        aux = cp.auxSysSolverBatch(sol, taus, wp, [0, 1])
+        assert int(aux["aux_status"][0]) == 0
+        Xa, Ua, PW = orc.aux(tg, X, U, Lam, th, back=back, fwd={})
+        loss, dl = orc.loss_grad(taus, wp[0], tg, X, Xa, sel=[0, 1])
+        assert abs(aux["loss"][0] - loss) < 1e-9 * max(1.0, loss)
+        assert _rel(aux["dtheta"][0], dl) < 1e-6, (mode, aux["dtheta"][0], dl)

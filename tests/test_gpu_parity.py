@@ -312,3 +312,30 @@ def test_rocket_batch1024_properties(torch_mod):
         assert _rel(_np(aux["dtheta"])[b], fx["dl_" + tag][b]) < 10 * GRAD_RTOL, (b, _np(aux["dtheta"])[b], fx["dl_" + tag][b])
     red = _np(oc.reduceBatch(aux["loss"], aux["dtheta"]))
     assert np.allclose(red[0], _np(aux["loss"]).sum(), rtol=1e-12) and np.allclose(red[1:], _np(aux["dtheta"]).sum(0), rtol=1e-10)
+
+
+def test_cartpole_vs_live_oracle(torch_mod):
+    """JinEnv.CartPole (no example script uses it) through the code generator and the kernels, against the
+    oracle run here (small: n=4, n_grid 20, two parameter vectors)."""
+    from oracle import models
+    from oracle.cpdp_oracle import Oracle
+    oc = _oc("cartpole", 20)
+    orc = Oracle(models.cartpole(), n_grid=20)
+    thetas = np.array([[1.5, 0.5, 1.0, 0.2, 0.3], [2.5, 1.0, 0.6, 0.1, 0.4]])
+    x0 = np.tile(np.array([0.0, 0.3, 0.0, 0.0]), (2, 1))
+    taus, wp = np.array([0.25, 0.7]), np.tile(np.array([[[0.1, 1.0], [0.0, 2.5]]]), (2, 1, 1))
+    sol = oc.cocSolverBatch(x0, 1.0, thetas)
+    assert (_np(sol["status"]) == 1).all()
+    modes = [(oc.MODE_RK45, {})] + ([(oc.MODE_BDF, {'method': 'BDF', 'jac': 'closed'})] if _has_bdf(oc) else [])
+    for b in range(2):
+        tg, X, U, Lam, info = orc.solve(x0[b], 1.0, thetas[b], return_info=True)
+        assert int(_np(sol["iters"])[b]) == info["iters"]
+        assert _rel(_np(sol["X"])[b], X) < TRAJ_RTOL and _rel(_np(sol["U"])[b], U) < TRAJ_RTOL
+        for mode, back in modes:
+            oc.aux_mode = mode
+            oc.rtol_back, oc.atol_back, oc.rtol_fwd, oc.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
+            aux = oc.auxSysSolverBatch(sol, taus, wp, [0, 1])
+            Xa, Ua, PW = orc.aux(tg, X, U, Lam, thetas[b], back=back, fwd={})
+            loss, dl = orc.loss_grad(taus, wp[b], tg, X, Xa, sel=[0, 1])
+            assert abs(_np(aux["loss"])[b] - loss) < 1e-8 * max(1.0, loss)
+            assert _rel(_np(aux["dtheta"])[b], dl) < GRAD_RTOL, (mode, b)

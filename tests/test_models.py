@@ -10,7 +10,7 @@ from lfsd_b200.sx import _to_matrix
 from oracle import models
 
 
-@pytest.mark.parametrize("name", ["pendulum", "robotarm", "rocket", "quadrotor"])
+@pytest.mark.parametrize("name", ["pendulum", "robotarm", "rocket", "quadrotor", "cartpole"])
 def test_product_models_equal_oracle_models(name):
     oc = standard.STANDARD[name]()
     om = getattr(models, name)()
