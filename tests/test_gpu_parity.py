@@ -339,3 +339,16 @@ def test_cartpole_vs_live_oracle(torch_mod):
             loss, dl = orc.loss_grad(taus, wp[b], tg, X, Xa, sel=[0, 1])
             assert abs(_np(aux["loss"])[b] - loss) < 1e-8 * max(1.0, loss)
             assert _rel(_np(aux["dtheta"])[b], dl) < GRAD_RTOL, (mode, b)
+
+
+def test_final_trajectory_export_vs_stored_files(torch_mod, tmp_path):
+    """QuadAlgorithm.py:299-343 on the GPU path at the stored learned parameter: the 101-point state / control
+    trajectories and the csv rows of the reference's stored result files."""
+    from lfsd_b200 import export
+    g = np.load(os.path.join(HERE, "golden", "quad_run.npz"))
+    oc = _oc("quadrotor", 25)
+    oc.pdata_value = g["goal_position"].reshape(1, 3)
+    ts, xs, us = export.final_trajectory(oc, g["ini_state"], float(g["horizon"]), g["parameter_trace"][-1])
+    assert np.array_equal(ts, g["time_steps"])
+    assert _rel(xs, g["opt_state_traj"]) < TRAJ_RTOL and _rel(us, g["opt_control_traj"]) < TRAJ_RTOL
+    assert np.abs(export.csv_array(ts, xs) - g["csv"]).max() < 1e-6 * np.abs(g["csv"]).max()
