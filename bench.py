@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--mode", default=None, choices=["bdf", "rk45"], help="backward Riccati integrator")
     ap.add_argument("--rtol", type=float, default=1e-3)
     ap.add_argument("--atol", type=float, default=1e-6)
+    ap.add_argument("--chunks", type=int, default=2, help="batch chunks on separate CUDA streams (1 = single stream)")
+    ap.add_argument("--rounds", type=int, default=8, help="Newton rounds launched per solve when chunks > 1 (no host sync)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-deadline", type=float, default=200.0, help="stop starting new CPU-baseline steps after this many seconds")
@@ -242,9 +244,15 @@ def run_ours(a):
     stats = {}
 
     def step(inp):
-        sol = oc.cocSolverBatch(inp["x0"], 1.0, inp["theta"], pdata=inp["goal"])
+        if a.chunks > 1:
+            # two halves of the shard on two streams, fixed number of Newton rounds (no host synchronisation): the tails
+            # of one half's kernels overlap the other half's work; results are bit-identical to the single-stream path
+            _, sol, aux = oc.gradIterBatch(inp["x0"], 1.0, inp["theta"], inp["taus"], inp["wp"], qb["sel"], pdata=inp["goal"],
+                                           rounds=a.rounds, chunks=a.chunks)
+        else:
+            sol = oc.cocSolverBatch(inp["x0"], 1.0, inp["theta"], pdata=inp["goal"])
+            aux = oc.auxSysSolverBatch(sol, inp["taus"], inp["wp"], qb["sel"])
         stats["rounds"] = lib.last_rounds()
-        aux = oc.auxSysSolverBatch(sol, inp["taus"], inp["wp"], qb["sel"])
         rows = torch.cat([aux["loss"].unsqueeze(1), aux["dtheta"]], dim=1)
         if world > 1:
             dist.all_gather_into_tensor(gathered, rows)     # the single exchange of the iteration (64 B / OCP)
@@ -272,6 +280,18 @@ def run_ours(a):
     sync_all()
     ev[0].record()
     for _ in range(a.steps):
+        red, sol, aux = step(resident)
+    ev[1].record()
+    sync_all()
+    ms = ev[0].elapsed_time(ev[1])
+    clocks = sampler.stop() if rank == 0 else None
+    sol_t, aux_t = sol, aux
+    # ---- phase times (single stream, each phase alone; explains `value`, is not part of it) -------------------------
+    for _ in range(2):                                    # untimed: allocates the single-stream workspace, warms the caches
+        s0 = oc.cocSolverBatch(resident["x0"], 1.0, resident["theta"], pdata=resident["goal"])
+        oc.auxSysSolverBatch(s0, resident["taus"], resident["wp"], qb["sel"])
+    sync_all()
+    for _ in range(a.steps):
         e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         e0.record()
         sol = oc.cocSolverBatch(resident["x0"], 1.0, resident["theta"], pdata=resident["goal"])
@@ -288,10 +308,7 @@ def run_ours(a):
         red = oc.reduceBatch(allrows[:, 0].contiguous(), allrows[:, 1:].contiguous())
         e3.record()
         ph.append((e0, e1, e2, e3))
-    ev[1].record()
     sync_all()
-    ms = ev[0].elapsed_time(ev[1])
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -375,11 +392,15 @@ def run_ours(a):
                                "rng default_rng(20210308); SURVEY.md 8d / BASELINE.json configs[4]" % (a.batch, " per GPU" if a.scaling == "weak" else " total"),
                    "n_grid": a.n_grid, "global_batch": B_total, "aux_mode": mode, "rtol_back": a.rtol, "atol_back": a.atol,
                    "parallelism": "dp%d contiguous shards, all-gather of per-OCP (loss,dtheta) rows + fixed-tree sum" % world,
+                   "streams": "%d chunk(s) of each shard on separate CUDA streams, %s" % (
+                       a.chunks, ("%d Newton rounds per solve, no host sync" % a.rounds) if a.chunks > 1 else "adaptive Newton rounds"),
                    "l2": "inputs larger than L2: per-step working set (~%.1f GB workspace + outputs) exceeds the 126 MB L2, "
                          "every step starts from the zero seed" % (lib.workspace_bytes(Bl, a.n_grid, 4) / 1e9)},
         "e2e": {"value": B_total * a.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": (r + 1) * 8},
-        "gpu_launches": a.steps * (2 + 4 * rounds + 2 + 1),
+        # timed region: per chunk k_solve_init + k_compact + 4 kernels per Newton round + backward + forward sweep, then one
+        # k_reduce_tree (single-stream mode launches only the rounds the adaptive solve needed)
+        "gpu_launches": a.steps * ((a.chunks * (2 + 4 * a.rounds + 2) + 1) if a.chunks > 1 else (2 + 4 * rounds + 2 + 1)),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "kernel": kname, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic, "traffic_source": traffic_src,

@@ -8,7 +8,6 @@
 //   CPDP_LAST_ERROR()                                           0 if no launch error
 #pragma once
 #include <cstddef>
-#include <cstdlib>
 #include <cstdint>
 
 namespace CPDP_NS {
@@ -162,8 +161,7 @@ static int cpdp_aux_impl(void* ws, size_t ws_bytes, int B, int N, int S, double 
             CPDP_PREPARE_SMEM(k_riccati_rk45, ric_bytes);
             CPDP_LAUNCH(k_riccati_rk45, B, AUX_THREADS, ric_bytes, st, a);
         } else {
-            static const size_t bdf_pad = getenv("CPDP_BDF_SMEM_PAD") ? (size_t)atol(getenv("CPDP_BDF_SMEM_PAD")) : 0;   // tuning knob: CTAs per SM
-            const size_t bdf_bytes = BDF_SMEM_BYTES + bdf_pad;
+            const size_t bdf_bytes = BDF_SMEM_BYTES;
             CPDP_PREPARE_SMEM(k_riccati_bdf, bdf_bytes);
             CPDP_LAUNCH(k_riccati_bdf, B, BDF_THREADS, bdf_bytes, st, a);
         }

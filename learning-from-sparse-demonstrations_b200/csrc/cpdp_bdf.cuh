@@ -849,7 +849,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
 }
 
 // k_riccati_bdf: backward sweep of COCSys.auxSysSolver as shipped (CPDP.py:327-338).
-CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, 7) k_riccati_bdf(AuxArgs a) {
+CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, 8) k_riccati_bdf(AuxArgs a) {
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     if (a.solve_status && (a.solve_status[b] == ST_NUMERIC || a.solve_status[b] == ST_RUNNING)) {
         if (tid == 0) a.aux_status[b] = 3;

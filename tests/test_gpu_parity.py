@@ -352,3 +352,24 @@ def test_final_trajectory_export_vs_stored_files(torch_mod, tmp_path):
     assert np.array_equal(ts, g["time_steps"])
     assert _rel(xs, g["opt_state_traj"]) < TRAJ_RTOL and _rel(us, g["opt_control_traj"]) < TRAJ_RTOL
     assert np.abs(export.csv_array(ts, xs) - g["csv"]).max() < 1e-6 * np.abs(g["csv"]).max()
+
+
+def test_chunked_streams_bit_identical(torch_mod):
+    """gradIterBatch(chunks=2|3, rounds=R): chunks of the batch on separate streams with separate workspaces give exactly
+    the single-stream results (per-problem independence + a reduction tree over the whole batch)."""
+    torch = torch_mod
+    from lfsd_b200 import synthetic
+    oc = _oc("quadrotor", 10)
+    oc.aux_mode = oc.MODE_BDF if _has_bdf(oc) else oc.MODE_RK45
+    qb = synthetic.quad_batch(96)
+    args = (qb["x0"], 1.0, qb["theta"], qb["taus"], qb["wp"], qb["sel"])
+    red1, sol1, aux1 = oc.gradIterBatch(*args, pdata=qb["goal"])
+    assert (_np(sol1["status"]) == 1).all() and int(_np(sol1["iters"]).max()) <= 9
+    for chunks in (2, 3):
+        red2, sol2, aux2 = oc.gradIterBatch(*args, pdata=qb["goal"], rounds=10, chunks=chunks)
+        torch.cuda.synchronize()
+        assert torch.equal(red1, red2)
+        for k in ("X", "U", "Lam", "iters", "status"):
+            assert torch.equal(sol1[k], sol2[k]), k
+        for k in ("Xa", "Ua", "loss", "dtheta", "counters"):
+            assert torch.equal(aux1[k], aux2[k]), k
