@@ -221,6 +221,9 @@ def run_ours(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes to stdout too
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     B_total = a.batch * world if a.scaling == "weak" else a.batch
     lo, hi = synthetic.shard_bounds(B_total, world, rank)
