@@ -62,25 +62,44 @@ CPDP_HD double interp_val(double ylo, double yhi, double xlo, double xhi, double
     return slope * (t - xlo) + ylo;
 }
 
+// Gauss-Jordan inverse with partial pivoting of a small matrix.  Every loop has a compile-time trip count and every
+// array index is static (the pivot row is swapped in through predicated exchanges), so the 2n^2 work array lives in
+// registers instead of local memory: it sits on the single-thread critical path of every ODE step.
 template <int n>
 CPDP_HD bool inv_small(const double* A, double* Ai) {
     double M[n][2 * n];
+#pragma unroll
     for (int i = 0; i < n; ++i)
+#pragma unroll
         for (int j = 0; j < n; ++j) { M[i][j] = A[i * n + j]; M[i][n + j] = (i == j) ? 1.0 : 0.0; }
+    bool ok = true;
+#pragma unroll
     for (int c = 0; c < n; ++c) {
         int p = c; double best = fabs(M[c][c]);
+#pragma unroll
         for (int i = c + 1; i < n; ++i) if (fabs(M[i][c]) > best) { best = fabs(M[i][c]); p = i; }
-        if (!(best > 0.0)) return false;
-        if (p != c) for (int j = 0; j < 2 * n; ++j) { double t = M[c][j]; M[c][j] = M[p][j]; M[p][j] = t; }
+        if (!(best > 0.0)) ok = false;
+#pragma unroll
+        for (int i = c + 1; i < n; ++i) {
+            const bool sw = (p == i);
+#pragma unroll
+            for (int j = 0; j < 2 * n; ++j) { const double a = M[c][j], b = M[i][j]; M[c][j] = sw ? b : a; M[i][j] = sw ? a : b; }
+        }
         const double d = 1.0 / M[c][c];
+#pragma unroll
         for (int j = 0; j < 2 * n; ++j) M[c][j] *= d;
+#pragma unroll
         for (int i = 0; i < n; ++i) if (i != c) {
             const double f = M[i][c];
-            if (f != 0.0) for (int j = 0; j < 2 * n; ++j) M[i][j] -= f * M[c][j];
+#pragma unroll
+            for (int j = 0; j < 2 * n; ++j) M[i][j] = (f != 0.0) ? M[i][j] - f * M[c][j] : M[i][j];
         }
     }
-    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Ai[i * n + j] = M[i][n + j];
-    return true;
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < n; ++j) Ai[i * n + j] = M[i][n + j];
+    return ok;
 }
 
 // Dormand-Prince 5(4) tableau as in scipy/integrate/_ivp/rk.py (class RK45)
@@ -132,13 +151,16 @@ struct AuxProblem {
     double dt; int N;
 };
 
-// interpolate (x,u,lam) at time t and evaluate the PMP matrices + inv(Huu) into slot; executed by ONE thread
-CPDP_D bool pmp_at(const AuxProblem& p, double t, double* xul, double* M) {
+// (x, u, lam) at time t by scipy's linear interp1d rule; element e of [x | u | lam]
+CPDP_D double xul_at(const AuxProblem& p, double t, int e) {
     const int lo = interp_lo(t, p.dt, p.N);
     const double xlo = p.dt * lo, xhi = p.dt * (lo + 1);
-    CPDP_LOOP for (int i = 0; i < NX; ++i) xul[i] = interp_val(p.X[(size_t)lo * NX + i], p.X[(size_t)(lo + 1) * NX + i], xlo, xhi, t);
-    CPDP_LOOP for (int i = 0; i < NU; ++i) xul[NX + i] = interp_val(p.U[(size_t)lo * NU + i], p.U[(size_t)(lo + 1) * NU + i], xlo, xhi, t);
-    CPDP_LOOP for (int i = 0; i < NX; ++i) xul[NX + NU + i] = interp_val(p.Lam[(size_t)lo * NX + i], p.Lam[(size_t)(lo + 1) * NX + i], xlo, xhi, t);
+    if (e < NX) return interp_val(p.X[(size_t)lo * NX + e], p.X[(size_t)(lo + 1) * NX + e], xlo, xhi, t);
+    if (e < NX + NU) return interp_val(p.U[(size_t)lo * NU + e - NX], p.U[(size_t)(lo + 1) * NU + e - NX], xlo, xhi, t);
+    return interp_val(p.Lam[(size_t)lo * NX + e - NX - NU], p.Lam[(size_t)(lo + 1) * NX + e - NX - NU], xlo, xhi, t);
+}
+// PMP matrices + inv(Huu) of one slot from its interpolated (x, u, lam); executed by ONE thread
+CPDP_D bool pmp_eval(const AuxProblem& p, const double* xul, double* M) {
     Model::pmp(xul, xul + NX, xul + NX + NU, p.th, p.pd, M);
     return inv_small<NU>(M + Model::PMP_HUU, M + Model::PMP_SIZE);
 }
@@ -263,8 +285,15 @@ CPDP_D bool aux_prepare(const AuxShared& s, const AuxProblem& p, const double* t
     const int tid = threadIdx.x, nt = blockDim.x;
     __syncthreads();
     double bad = 0.0;
+    // the interpolations (one division each) are spread over the CTA; only the generated model code and the m x m
+    // inverse stay on a single thread per slot
+    CPDP_LOOP for (int q = tid; q < cnt * (2 * NX + NU); q += nt) {
+        const int sl = q / (2 * NX + NU), e = q % (2 * NX + NU);
+        s.xul[q] = xul_at(p, times[sl], e);
+    }
+    __syncthreads();
     if (tid < cnt) {
-        if (!pmp_at(p, times[tid], s.xul + (size_t)tid * (2 * NX + NU), s.M + (size_t)tid * MSZ)) bad = 1.0;
+        if (!pmp_eval(p, s.xul + (size_t)tid * (2 * NX + NU), s.M + (size_t)tid * MSZ)) bad = 1.0;
     }
     if (FWD) {
         CPDP_LOOP for (int q = tid; q < cnt * NYR; q += nt) {
