@@ -17,7 +17,8 @@ def _declared_symbols():
 
 
 @pytest.mark.parametrize("model,dims", [("pendulum", (2, 1, 3, 0)), ("robotarm", (4, 2, 5, 0)),
-                                        ("rocket", (13, 3, 12, 0)), ("quadrotor", (13, 4, 7, 3))])
+                                        ("rocket", (13, 3, 12, 0)), ("quadrotor", (13, 4, 7, 3)),
+                                        ("cartpole", (4, 1, 5, 0))])
 def test_library_exports(model, dims):
     so = os.path.join(_capi.LIB_DIR, "libcpdp_%s.so" % model)
     if not os.path.exists(so):
