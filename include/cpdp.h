@@ -90,6 +90,10 @@ int cpdp_reduce(const double* loss, const double* dtheta, int B, double* scratch
 
 const char* cpdp_error_string(int code);
 
+/* "CPDP_BUILD_DIGEST=<sha1>" of the generated model header, kernel sources and compiler flags this library was built
+ * from (the host package uses it to recognise an up-to-date prebuilt library). */
+const char* cpdp_build_digest(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,10 @@ GEN_DIR = os.path.join(CSRC, "generated")
 LIB_DIR = os.path.join(_PKG, "lib")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden"] + os.environ.get("CPDP_EXTRA_NVCC_FLAGS", "").split()
+              "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
+# developer knob for tuning experiments (e.g. -DCPDP_HESS_MINB=2): forces a rebuild here and is deliberately NOT part of the
+# build digest, so that a variant built in this container is used as it is on a GPU box that does not set the variable
+EXTRA_NVCC_FLAGS = os.environ.get("CPDP_EXTRA_NVCC_FLAGS", "").split()
 
 STATUS_NAMES = {0: "running", 1: "converged", 2: "max_iter", 3: "linesearch_fail", 4: "numeric"}
 
@@ -23,6 +26,9 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _d = ctypes.c_double
 _sz = ctypes.c_size_t
+
+
+_DIGEST_MARK = "CPDP_BUILD_DIGEST="
 
 
 class CpdpError(RuntimeError):
@@ -48,8 +54,12 @@ def build_model_library(name, header_text, force=False, verbose=False):
     so = os.path.join(LIB_DIR, "libcpdp_%s.so" % name)
     stamp = so + ".stamp"
     digest = hashlib.sha1((header_text + _sources_digest() + " ".join(NVCC_FLAGS)).encode()).hexdigest()
-    if not force and os.path.exists(so) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
-        return so
+    # up to date?  The digest of (model header, kernel sources, flags) is compiled INTO the library (cpdp_build_digest), so a
+    # prebuilt .so is recognised wherever it travels without any side file (git-ignored stamp files do not reach a GPU box).
+    if not force and not EXTRA_NVCC_FLAGS and os.path.exists(so):
+        with open(so, "rb") as f:
+            if (_DIGEST_MARK + digest).encode() in f.read():
+                return so
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise CpdpError("libcpdp_%s.so is missing and nvcc was not found; the CUDA extension is required "
@@ -57,7 +67,8 @@ def build_model_library(name, header_text, force=False, verbose=False):
     with open(hdr, "w") as f:
         f.write(header_text)
     ns = "cpdp_" + "".join(ch if ch.isalnum() else "_" for ch in name)
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", CSRC, "-DCPDP_NS=%s" % ns, "-DCPDP_MODEL_HEADER=\"%s\"" % hdr,
+    cmd = [nvcc] + NVCC_FLAGS + EXTRA_NVCC_FLAGS + ["-I", CSRC, "-DCPDP_NS=%s" % ns, "-DCPDP_MODEL_HEADER=\"%s\"" % hdr,
+                                 "-DCPDP_BUILD_DIGEST=\"%s%s\"" % (_DIGEST_MARK, digest),
                                  os.path.join(CSRC, "cpdp_lib.cu"), "-o", so]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

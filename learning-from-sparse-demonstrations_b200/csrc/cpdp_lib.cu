@@ -55,6 +55,13 @@ static void cpdp_prepare_smem(K kernel, size_t bytes) {
 #define CPDP_LAST_ERROR() cpdp_take_error()
 #include "cpdp_api.inl"
 
+// Digest of (generated model header, kernel sources, compiler flags) this library was built from; lfsd_b200._capi looks
+// for the marker in the file to decide whether a prebuilt library is up to date.
+#ifndef CPDP_BUILD_DIGEST
+#define CPDP_BUILD_DIGEST "CPDP_BUILD_DIGEST=unknown"
+#endif
+extern "C" CPDP_API const char* cpdp_build_digest(void) { return CPDP_BUILD_DIGEST; }
+
 extern "C" CPDP_API const char* cpdp_error_string(int code) {
     if (code < 0) {
         switch (code) {
