@@ -53,7 +53,7 @@ static WsLayout ws_carve(char* base, int B, int N, int S) {
     a.act = takeI(B);
     a.nact = takeI(1);
     w.PW = takeD(BN1 * NYR);
-    w.Dbdf = takeD((size_t)B * BDF_WS_ROWS * NYR);      // k_riccati_bdf: differences array + scale, psi, d rows per problem
+    w.Dbdf = takeD((size_t)B * BDF_WS_DOUBLES);      // k_riccati_bdf: differences array + scale, psi, d rows per problem
     w.bytes = off;
     return w;
 }

@@ -28,11 +28,24 @@
 
 namespace CPDP_NS {
 
-constexpr int BDF_THREADS = 64;
+#ifndef CPDP_BDF_THREADS
+#define CPDP_BDF_THREADS 32
+#endif
+#ifndef CPDP_BDF_MINB
+#define CPDP_BDF_MINB 8
+#endif
+constexpr int BDF_THREADS = CPDP_BDF_THREADS;
+// With one warp per problem (the shipped shape) every CTA-wide barrier of this file is a warp barrier.
+#if defined(__CUDACC__) && CPDP_BDF_THREADS == 32
+#define BDF_SYNC() __syncwarp()
+#else
+#define BDF_SYNC() __syncthreads()
+#endif
 constexpr int BDF_MAX_ORDER = 5;
 constexpr int BDF_NEWTON_MAXITER = 4;
 constexpr int BDF_NROWS = BDF_MAX_ORDER + 3;
 constexpr int BDF_WS_ROWS = BDF_NROWS + 3;      // workspace rows per problem: differences array + scale, psi, d
+constexpr int BDF_WS_DOUBLES = BDF_WS_ROWS * NYR;
 
 struct BdfShared {
     double* Tr; double* Ti;   // [NX*NX]  Schur form L = Z T Z^H (T upper triangular)
@@ -65,7 +78,8 @@ CPDP_HD double bdf_error_const(int k) { return bdf_kappa(k) * bdf_gamma(k) + 1.0
 // Shared-memory layout.  Every array sits at a COMPILE-TIME offset of the dynamic shared-memory block, so the
 // out-of-line pieces below rebuild their views from constants (no pointer structs in local memory, no registers).
 constexpr int BDF_GSZ = (2 * NX * NX > NYR) ? 2 * NX * NX : NYR;      // (Gr, Gi) block; doubles as bdf_solve's NYR scratch
-constexpr int BDF_SMEM_DOUBLES = MSZ + (2 * NX + NU) + (BDF_THREADS + 2) + NX * NX + 2 * NU * NX + NU * NP       // AuxShared
+constexpr int BDF_RED = (BDF_THREADS > 64 ? BDF_THREADS : 64) + 2;   // block_reduce scratch; the emulated sweep uses 64 entries
+constexpr int BDF_SMEM_DOUBLES = MSZ + (2 * NX + NU) + BDF_RED + NX * NX + 2 * NU * NX + NU * NP       // AuxShared
                                  + 5 * NX * NX + 4 * NX + BDF_GSZ + 2 * NT + NX * NP + NX * NX                           // Schur data, Cm, Winv
                                  + 2 * NYR + 108 + 8 + 2;                                                        // y, dy, RU, tms, flag
 constexpr int BDF_SMEM_INTS = 2 * NT + SPTAB_INTS;
@@ -74,9 +88,10 @@ static_assert(NX * NU <= NX * NX, "GH aliases an NX x NX scratch matrix");
 
 CPDP_D void bdf_layout(double* smem, AuxShared& s, BdfShared& bs, double*& tms) {
     double* ptr = smem;
-    s.M = carve(ptr, MSZ);                       // one PMP slot: every Newton iterate of a step shares t_new
+    s.M = carve(ptr, MSZ);                       // one PMP slot: every Newton iterate of a step shares t_new (kept in shared
+                                                 // memory: in the L2 workspace it bought 10 CTAs per SM and no throughput)
     s.xul = carve(ptr, 2 * NX + NU);
-    s.red = carve(ptr, BDF_THREADS + 2);
+    s.red = carve(ptr, BDF_RED);
     s.P = carve(ptr, NX * NX);
     s.Y = carve(ptr, NU * NX);
     s.Yp = carve(ptr, NU * NX);
@@ -100,23 +115,34 @@ CPDP_D void bdf_layout(double* smem, AuxShared& s, BdfShared& bs, double*& tms) 
 }
 #define BDF_LAYOUT() CPDP_DYN_SMEM(smem); AuxShared s; BdfShared bs; double* tms; bdf_layout(smem, s, bs, tms); (void)tms
 
-CPDP_D double bdf_reduce(double v, bool is_max) { BDF_LAYOUT(); return block_reduce(v, s.red, is_max); }
+CPDP_D double bdf_reduce(double v, bool is_max) {
+#if defined(__CUDACC__) && CPDP_BDF_THREADS == 32
+    // one warp: block_reduce's xor butterfly alone (identical operation order, no shared memory, no barrier)
+    CPDP_LOOP for (int o = 16; o > 0; o >>= 1) {
+        const double x = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmax(v, x) : (v + x);
+    }
+    return v;
+#else
+    BDF_LAYOUT();
+    return block_reduce(v, s.red, is_max);
+#endif
+}
 CPDP_D double bdf_pow(double x, double y) { return pow(x, y); }
 
 // out-of-line instances of the shared right-hand side / PMP evaluation (one copy each instead of three)
-CPDP_D_NOINLINE void bdf_rhs(const double* yin, double* ydot) { BDF_LAYOUT(); riccati_rhs(s, s.M, yin, ydot); }
-CPDP_D_NOINLINE bool bdf_prepare(const AuxProblem p) { BDF_LAYOUT(); return aux_prepare<false>(s, p, tms, 1); }
+CPDP_D_NOINLINE void bdf_rhs(const double* M, const double* yin, double* ydot) { BDF_LAYOUT(); riccati_rhs(s, M, yin, ydot); }
+CPDP_D_NOINLINE bool bdf_prepare(const AuxProblem p, double* M) { BDF_LAYOUT(); (void)M; return aux_prepare<false>(s, p, tms, 1); }
 
 // Closed-form Jacobian data at (PMP matrices M, packed state yJ):  L = A' - P R,  C = R W - r_
 // with A = fx - fu Huu^{-1} Hxu', R = fu Huu^{-1} fu', r_ = fe - fu Huu^{-1} Hue  (CPDP.py:262-270).
-CPDP_D_NOINLINE void bdf_jacobian(const double* yJ) {
+CPDP_D_NOINLINE void bdf_jacobian(const double* M, const double* yJ) {
     BDF_LAYOUT();
-    const double* M = s.M;
     const int tid = threadIdx.x, nt = blockDim.x;
     const double* fx = M + Model::PMP_FX; const double* fu = M + Model::PMP_FU; const double* fe = M + Model::PMP_FE;
     const double* Hxu = M + Model::PMP_HXU; const double* Hue = M + Model::PMP_HUE; const double* Hinv = M + Model::PMP_SIZE;
     const double* Wm = yJ + NT;
-    __syncthreads();
+    BDF_SYNC();
     CPDP_LOOP for (int i = tid; i < NX * NX; i += nt) {
         const int r_ = i / NX, c = i % NX;
         s.P[i] = yJ[r_ <= c ? tri(r_, c) : tri(c, r_)];
@@ -127,14 +153,14 @@ CPDP_D_NOINLINE void bdf_jacobian(const double* yJ) {
         CPDP_LOOP for (int b2 = 0; b2 < NU; ++b2) acc += fu[r_ * NU + b2] * Hinv[b2 * NU + a];
         bs.GH[i] = acc;
     }
-    __syncthreads();
+    BDF_SYNC();
     CPDP_LOOP for (int i = tid; i < NX * NX; i += nt) {
         const int r_ = i / NX, c = i % NX;
         double a1 = fx[i], a2 = 0.0;
         CPDP_LOOP for (int a = 0; a < NU; ++a) { a1 -= bs.GH[r_ * NU + a] * Hxu[c * NU + a]; a2 += bs.GH[r_ * NU + a] * fu[c * NU + a]; }
         bs.Am[i] = a1; bs.Rm[i] = a2;
     }
-    __syncthreads();
+    BDF_SYNC();
     CPDP_LOOP for (int i = tid; i < NX * NX + NX * NP; i += nt) {
         if (i < NX * NX) {
             const int r_ = i / NX, a = i % NX;
@@ -149,7 +175,7 @@ CPDP_D_NOINLINE void bdf_jacobian(const double* yJ) {
             bs.Cm[e] = acc;
         }
     }
-    __syncthreads();
+    BDF_SYNC();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -304,10 +330,10 @@ CPDP_D_NOINLINE bool bdf_schur() {
     BDF_LAYOUT();
     constexpr int n = NX;
     const int tid = threadIdx.x, nt = blockDim.x;
-    __syncthreads();
+    BDF_SYNC();
     CPDP_LOOP for (int i = tid; i < n * n; i += nt) { bs.Tr[i] = bs.Lm[i]; bs.Ti[i] = 0.0; }
     if (tid == 0) bs.flag[0] = 1;
-    __syncthreads();
+    BDF_SYNC();
 #ifdef __CUDACC__
     if (tid < 32)
 #endif
@@ -360,7 +386,7 @@ CPDP_D_NOINLINE bool bdf_schur() {
             CPDP_W0_SYNC();
         }
     }
-    __syncthreads();
+    BDF_SYNC();
     return bs.flag[0] != 0;
 }
 
@@ -406,7 +432,7 @@ CPDP_D_NOINLINE bool bdf_factor(const double c) {
     BDF_LAYOUT();
     constexpr int n = NX;
     const int tid = threadIdx.x, nt = blockDim.x;
-    __syncthreads();
+    BDF_SYNC();
     double bad = 0.0;
     if (tid < n) {                                   // column tid of S = (I + c T)^{-1}  (upper triangular) -> (Fr, Fi)
         const int j = tid;
@@ -457,16 +483,16 @@ CPDP_D_NOINLINE bool bdf_factor(const double c) {
         }
         bs.Gr[e] = acc;
     }
-    __syncthreads();
+    BDF_SYNC();
     mm_nn(bs.Zr, bs.Gr, bs.Fr);                                // F = Q Sr
-    __syncthreads();
+    BDF_SYNC();
     CPDP_LOOP for (int e = tid; e < n * n; e += nt) {          // Winv = F Q^T
         const int i = e / n, l = e % n;
         double acc = 0.0;
         CPDP_LOOP for (int k = 0; k < n; ++k) acc += bs.Fr[i * n + k] * bs.Zr[l * n + k];
         bs.Winv[e] = acc;
     }
-    __syncthreads();
+    BDF_SYNC();
     return true;
 }
 
@@ -476,20 +502,20 @@ CPDP_D_NOINLINE void bdf_solve(const double c) {
     double* dy = bs.dy; double* tmp = bs.tmp;
     constexpr int n = NX;
     const int tid = threadIdx.x, nt = blockDim.x;
-    __syncthreads();
+    BDF_SYNC();
     CPDP_LOOP for (int q = tid; q < NT; q += nt) {             // B = sym(dy[0:NT]) expanded -> P
         const int i = s.ti[q], j = s.tj[q];
         const double v = dy[q];
         s.P[i * n + j] = v; s.P[j * n + i] = v;
     }
-    __syncthreads();
+    BDF_SYNC();
     mm_nn(s.P, bs.Zr, bs.Fr);                                  // F = B Q   (real)
-    __syncthreads();
+    BDF_SYNC();
     {                                                          // Cr = Q^T F  (real symmetric, both triangles) -> Fi
         double* Cr = bs.Fi;
         mm_tri<true>(s, bs.Zr, bs.Fr, [Cr](int, int i, int j, double v) { Cr[i * n + j] = v; Cr[j * n + i] = v; });
     }
-    __syncthreads();
+    BDF_SYNC();
     CPDP_LOOP for (int q = tid; q < NT; q += nt) {             // C = G Cr G^H (upper triangle) -> (Gr, Gi)
         const int i = s.ti[q], j = s.tj[q];
         const int pi = (int)bs.pi[i], pj = (int)bs.pi[j];
@@ -502,7 +528,7 @@ CPDP_D_NOINLINE void bdf_solve(const double c) {
         bs.Gr[i * n + j] = ujr * gj_a + (upr * gj_br - upi * gj_bi);
         bs.Gi[i * n + j] = uji * gj_a + (upr * gj_bi + upi * gj_br);
     }
-    __syncthreads();
+    BDF_SYNC();
     // ---- (1/2 + cT) Y + Y (1/2 + cT)^H = C along anti-diagonals i + j = d (warp 0; 4 lanes per entry); Y overwrites C,
     //      both triangles are kept (Y is Hermitian)
 #ifdef __CUDACC__
@@ -564,7 +590,7 @@ CPDP_D_NOINLINE void bdf_solve(const double c) {
             CPDP_W0_SYNC();
         }
     }
-    __syncthreads();
+    BDF_SYNC();
     CPDP_LOOP for (int q = tid; q < NT; q += nt) {             // Yr = Re(G^H Y G)  (real symmetric, both triangles) -> Fr
         const int i = s.ti[q], j = s.tj[q];
         const int pi = (int)bs.pi[i], pj = (int)bs.pi[j];
@@ -577,14 +603,14 @@ CPDP_D_NOINLINE void bdf_solve(const double c) {
         const double v = tjr * bj_r + (tpr * bp_r - tpi * bp_i);
         bs.Fr[i * n + j] = v; bs.Fr[j * n + i] = v;
     }
-    __syncthreads();
+    BDF_SYNC();
     mm_nn(bs.Zr, bs.Fr, bs.Fi);                                // F2 = Q Yr -> Fi
-    __syncthreads();
+    BDF_SYNC();
     {                                                          // X = F2 Q^T, upper triangle -> tmp and expanded -> P
         double* Pm = s.P;
         mm_tri<false>(s, bs.Fi, bs.Zr, [tmp, Pm](int q, int i, int l, double v) { tmp[q] = v; Pm[i * n + l] = v; Pm[l * n + i] = v; });
     }
-    __syncthreads();
+    BDF_SYNC();
     double* dW = dy + NT;
     CPDP_LOOP for (int e = tid; e < NX * NP; e += nt) {                  // B_W + c X C
         const int i = e / NP, k = e % NP;
@@ -593,14 +619,14 @@ CPDP_D_NOINLINE void bdf_solve(const double c) {
         tmp[NT + e] = dW[e] + c * acc;
     }
     CPDP_LOOP for (int k = tid; k < NT; k += nt) dy[k] = tmp[k];
-    __syncthreads();
+    BDF_SYNC();
     CPDP_LOOP for (int e = tid; e < NX * NP; e += nt) {                  // dW = (I + cL)^{-1} (...)
         const int i = e / NP, k = e % NP;
         double acc = 0.0;
         CPDP_LOOP for (int a = 0; a < NX; ++a) acc += bs.Winv[i * NX + a] * tmp[NT + a * NP + k];
         dW[e] = acc;
     }
-    __syncthreads();
+    BDF_SYNC();
 }
 
 // change_D (bdf.py:18-33): D[:order+1] <- (R U)' D[:order+1]
@@ -609,7 +635,7 @@ CPDP_D_NOINLINE void bdf_change_D(double* D, const int order, const double facto
     bs.D = D;
     const int tid = threadIdx.x, nt = blockDim.x;
     double* R = bs.RU + 36; double* U = bs.RU + 72;         // 6 x 6 scratch
-    __syncthreads();
+    BDF_SYNC();
     if (tid <= order) {                                     // column tid of R and U: cumprod down the rows (compute_R)
         const int j = tid;
         R[j] = 1.0; U[j] = 1.0;
@@ -618,16 +644,16 @@ CPDP_D_NOINLINE void bdf_change_D(double* D, const int order, const double facto
             U[i * 6 + j] = (j == 0) ? 0.0 : U[(i - 1) * 6 + j] * (((double)(i - 1) - (double)j) / i);
         }
     }
-    __syncthreads();
-    if (tid < 36) {
-        const int i = tid / 6, j = tid % 6;
+    BDF_SYNC();
+    CPDP_LOOP for (int e = tid; e < 36; e += nt) {
+        const int i = e / 6, j = e % 6;
         if (i <= order && j <= order) {
             double acc = 0.0;
             CPDP_LOOP for (int k = 0; k <= order; ++k) acc += R[i * 6 + k] * U[k * 6 + j];
             bs.RU[i * 6 + j] = acc;
         }
     }
-    __syncthreads();
+    BDF_SYNC();
     CPDP_LOOP for (int q = tid; q < NYR; q += nt) {
         double v[BDF_MAX_ORDER + 1];
 #pragma unroll
@@ -642,7 +668,7 @@ CPDP_D_NOINLINE void bdf_change_D(double* D, const int order, const double facto
             }
         }
     }
-    __syncthreads();
+    BDF_SYNC();
 }
 
 // RMS norm of v/scale over the FULL (n^2 + n r) state (off-diagonal entries of the packed P count twice)
@@ -663,10 +689,10 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
     const double EPS = 2.220446049250313e-16;
     // ---- __init__ (bdf.py:200-257)
     if (tid == 0) tms[0] = t0;
-    if (!bdf_prepare(p)) return 2;
+    if (!bdf_prepare(p, s.M)) return 2;
     double* f0 = bs.d;                 // f(t0, y0) parked in the (not yet used) d row
-    bdf_rhs(y, f0); ++cnt[0];
-    bdf_jacobian(y); ++cnt[3];
+    bdf_rhs(s.M, y, f0); ++cnt[0];
+    bdf_jacobian(s.M, y); ++cnt[3];
     if (!bdf_schur()) return 4;
     double h_abs;
     {
@@ -683,8 +709,8 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
         h0 = fmin(h0, interval_length);
         CPDP_LOOP for (int i = tid; i < NYR; i += nt) bs.dy[i] = y[i] + h0 * dir * f0[i];
         if (tid == 0) tms[0] = t0 + h0 * dir;
-        if (!bdf_prepare(p)) return 2;
-        bdf_rhs(bs.dy, bs.tmp); ++cnt[0];
+        if (!bdf_prepare(p, s.M)) return 2;
+        bdf_rhs(s.M, bs.dy, bs.tmp); ++cnt[0];
         double a2 = 0.0;
         CPDP_LOOP for (int i = tid; i < NYR; i += nt) {
             const double sc = atol + fabs(y[i]) * rtol;
@@ -699,7 +725,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
     }
     const double newton_tol = fmax(10 * EPS / rtol, fmin(0.03, sqrt(rtol)));
     CPDP_LOOP for (int i = tid; i < NYR; i += nt) { bs.D[i] = y[i]; bs.D[NYR + i] = f0[i] * h_abs * dir; }
-    __syncthreads();
+    BDF_SYNC();
     int order = 1, n_equal_steps = 0;
     bool lu_valid = false;
     double c_lu = 0.0;                 // the c the current LU was built with (scipy keeps a stale LU after an error rejection)
@@ -744,7 +770,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                 bs.psi[i] = ps / al;
             }
             if (tid == 0) tms[0] = t_new;
-            if (!bdf_prepare(p)) return 2;      // PMP matrices at t_new (every Newton iterate shares them)
+            if (!bdf_prepare(p, s.M)) return 2;      // PMP matrices at t_new (every Newton iterate shares them)
             const double c = h / al;
             bool converged = false;
             while (!converged) {
@@ -754,11 +780,11 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                 }
                 // ---- solve_bdf_system (bdf.py:36-75)
                 CPDP_LOOP for (int i = tid; i < NYR; i += nt) bs.d[i] = 0.0;
-                __syncthreads();
+                BDF_SYNC();
                 double dy_norm_old = -1.0;
                 int k = 0;
                 CPDP_LOOP for (k = 0; k < BDF_NEWTON_MAXITER; ++k) {
-                    bdf_rhs(bs.y, bs.dy); ++cnt[0];
+                    bdf_rhs(s.M, bs.y, bs.dy); ++cnt[0];
                     double fin = 0.0;
                     CPDP_LOOP for (int i = tid; i < NYR; i += nt) {
                         const double fv = bs.dy[i];
@@ -773,7 +799,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                     const double rate = have_rate ? dy_norm / dy_norm_old : 0.0;
                     if (have_rate && (rate >= 1 || bdf_pow(rate, (double)(BDF_NEWTON_MAXITER - k)) / (1 - rate) * dy_norm > newton_tol)) break;
                     CPDP_LOOP for (int i = tid; i < NYR; i += nt) { bs.y[i] += bs.dy[i]; bs.d[i] += bs.dy[i]; }
-                    __syncthreads();
+                    BDF_SYNC();
                     if (dy_norm == 0 || (have_rate && rate / (1 - rate) * dy_norm < newton_tol)) { converged = true; break; }
                     dy_norm_old = dy_norm;
                 }
@@ -786,7 +812,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                         CPDP_LOOP for (int k = 0; k <= order; ++k) yp += bs.D[(size_t)k * NYR + i];
                         bs.y[i] = yp;
                     }
-                    bdf_jacobian(bs.y); ++cnt[3];
+                    bdf_jacobian(s.M, bs.y); ++cnt[3];
                     if (!bdf_schur()) return 4;
                     lu_valid = false;
                     current_jac = true;
@@ -801,7 +827,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
             }
             safety = 0.9 * (2 * BDF_NEWTON_MAXITER + 1) / (double)(2 * BDF_NEWTON_MAXITER + n_iter);
             CPDP_LOOP for (int i = tid; i < NYR; i += nt) bs.scale[i] = atol + rtol * fabs(bs.y[i]);
-            __syncthreads();
+            BDF_SYNC();
             error_norm = bdf_norm(bs.d, bs.scale, bdf_error_const(order));
             if (!(error_norm == error_norm)) return 2;
             if (error_norm > 1) {
@@ -824,7 +850,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
             bs.D[(size_t)(order + 1) * NYR + i] = dv;
             CPDP_LOOP for (int k = order; k >= 0; --k) bs.D[(size_t)k * NYR + i] += bs.D[(size_t)(k + 1) * NYR + i];
         }
-        __syncthreads();
+        BDF_SYNC();
         if (n_equal_steps < order + 1) continue;
         double error_m_norm = INFINITY, error_p_norm = INFINITY;
         if (order > 1) error_m_norm = bdf_norm(bs.D + (size_t)order * NYR, bs.scale, bdf_error_const(order - 1));
@@ -844,12 +870,12 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
     }
     // solve_ivp(t_eval=[t1]) returns the dense output at the step end = D[0] (bdf.py:462-484)
     CPDP_LOOP for (int i = tid; i < NYR; i += nt) y[i] = bs.D[i];
-    __syncthreads();
+    BDF_SYNC();
     return 0;
 }
 
 // k_riccati_bdf: backward sweep of COCSys.auxSysSolver as shipped (CPDP.py:327-338).
-CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, 8) k_riccati_bdf(AuxArgs a) {
+CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, CPDP_BDF_MINB) k_riccati_bdf(AuxArgs a) {
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     if (a.solve_status && (a.solve_status[b] == ST_NUMERIC || a.solve_status[b] == ST_RUNNING)) {
         if (tid == 0) a.aux_status[b] = 3;
@@ -866,7 +892,7 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, 8) k_riccati_bdf(AuxArgs a) {
     }
     CPDP_LOOP for (int q = tid; q < MSZ; q += nt) s.M[q] = 0.0;
     aux_tables(s, (int*)s.ti + 2 * NT);
-    bs.D = a.Dws + (size_t)b * BDF_WS_ROWS * NYR;
+    bs.D = a.Dws + (size_t)b * BDF_WS_DOUBLES;
     bs.scale = bs.D + (size_t)BDF_NROWS * NYR; bs.psi = bs.scale + NYR; bs.d = bs.psi + NYR;
     double* y = bs.y;                            // state at the interval boundaries
     const int N = a.N;
@@ -882,19 +908,19 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, 8) k_riccati_bdf(AuxArgs a) {
         CPDP_LOOP for (int i = 0; i < NX; ++i) xT[i] = interp_val(p.X[(size_t)lo * NX + i], p.X[(size_t)(lo + 1) * NX + i], p.dt * lo, p.dt * (lo + 1), tN);
         Model::term2(xT, p.th, p.pd, s_hxx, s_hxe);
     }
-    __syncthreads();
+    BDF_SYNC();
     CPDP_LOOP for (int q = tid; q < NYR; q += nt) {
         const double v = (q < NT) ? 0.5 * (s_hxx[s.ti[q] * NX + s.tj[q]] + s_hxx[s.tj[q] * NX + s.ti[q]]) : s_hxe[q - NT];
         y[q] = v;
         PW[(size_t)N * NYR + q] = v;
     }
-    __syncthreads();
+    BDF_SYNC();
     int cnt[4] = {0, 0, 0, 0};
     int st = 0;
     CPDP_LOOP for (int k = N; k >= 1 && st == 0; --k) {
         st = bdf_interval(s, bs, p, p.dt * k, p.dt * (k - 1), a.rtol_b, a.atol_b, y, tms, cnt);
         CPDP_LOOP for (int q = tid; q < NYR; q += nt) PW[(size_t)(k - 1) * NYR + q] = y[q];
-        __syncthreads();
+        BDF_SYNC();
     }
 #ifdef CPDP_DEBUG_DUMP
     if (st == 4) {
