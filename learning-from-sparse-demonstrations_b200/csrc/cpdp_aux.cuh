@@ -20,7 +20,10 @@ constexpr int NYF = NX * NP;                   // forward state
 constexpr int NFULL_R = NX * NX + NX * NP;
 constexpr int MSZ = Model::PMP_SIZE + NU * NU; // dense PMP matrices + inverse of Huu
 constexpr int NSLOT = 5;                       // distinct stage times of one Dormand-Prince step
-constexpr int AUX_THREADS = 64;
+#ifndef CPDP_AUX_THREADS
+#define CPDP_AUX_THREADS 64
+#endif
+constexpr int AUX_THREADS = CPDP_AUX_THREADS;
 constexpr int MAX_SEL = 16;
 constexpr int NCOUNTERS = 6;                    // per-problem counters: back rhs, back steps, fwd rhs, fwd steps, back LU, back Jacobians
 
