@@ -35,7 +35,7 @@ struct AuxArgs {
     const double* X; const double* U; const double* Lam;   // [B][N+1][.]
     double rtol_b, atol_b, rtol_f, atol_f;
     double* PW;            // [B][N+1][NYR]   packed Riccati nodes
-    double* Dws;           // [B][11][NYR]    BDF differences arrays + scale, psi, d rows (workspace; mode 1 only)
+    double* Dws;           // [B][11][NYR]    BDF differences arrays + scale, psi, d rows (L2-resident workspace; mode 1 only)
     double* Xa;            // [B][N+1][NX*NP] aux state nodes  (dx/dtheta)
     double* Ua;            // [B][N+1][NU*NP] aux control nodes
     int W, D;              // waypoints per problem, observed dims

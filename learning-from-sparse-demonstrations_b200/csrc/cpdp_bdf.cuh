@@ -390,6 +390,15 @@ CPDP_D_NOINLINE bool bdf_schur() {
     return bs.flag[0] != 0;
 }
 
+// inner 13-term loops of the small products: rolled by default, -DCPDP_MM_UNROLL=k unrolls them k times (tuning knob)
+#ifdef CPDP_MM_UNROLL
+#define CPDP_MM_PRAGMA(k) _Pragma(#k)
+#define CPDP_MM_LOOP2(k) CPDP_MM_PRAGMA(unroll k)
+#define CPDP_MM_LOOP CPDP_MM_LOOP2(CPDP_MM_UNROLL)
+#else
+#define CPDP_MM_LOOP CPDP_LOOP
+#endif
+
 // Small dense products with three (two) outputs per thread in flight: the rolled 13-term dot products are latency
 // bound, independent accumulators overlap their shared-memory loads and DFMA chains without unrolling the loop.
 //   mm_nn:      out[i][k] = sum_j A[i][j] B[j][k]                       all n*n outputs
@@ -403,7 +412,7 @@ CPDP_D void mm_nn(const double* A, const double* B, double* out) {
         const double* a0 = A + (f0 / n) * n; const double* a1 = A + (f1 / n) * n; const double* a2 = A + (f2 / n) * n;
         const double* b0 = B + f0 % n; const double* b1 = B + f1 % n; const double* b2 = B + f2 % n;
         double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-        CPDP_LOOP for (int j = 0; j < n; ++j) { c0 += a0[j] * b0[j * n]; c1 += a1[j] * b1[j * n]; c2 += a2[j] * b2[j * n]; }
+        CPDP_MM_LOOP for (int j = 0; j < n; ++j) { c0 += a0[j] * b0[j * n]; c1 += a1[j] * b1[j * n]; c2 += a2[j] * b2[j * n]; }
         if (e0 < n * n) out[e0] = c0;
         if (e1 < n * n) out[e1] = c1;
         if (e2 < n * n) out[e2] = c2;
@@ -421,7 +430,7 @@ CPDP_D void mm_tri(const AuxShared& s, const double* A, const double* B, Store s
         const double* a1 = TA ? A + i1 : A + i1 * n; const double* b1 = TA ? B + j1 : B + j1 * n;
         constexpr int st = TA ? n : 1;
         double c0 = 0.0, c1 = 0.0;
-        CPDP_LOOP for (int k = 0; k < n; ++k) { c0 += a0[k * st] * b0[k * st]; c1 += a1[k * st] * b1[k * st]; }
+        CPDP_MM_LOOP for (int k = 0; k < n; ++k) { c0 += a0[k * st] * b0[k * st]; c1 += a1[k * st] * b1[k * st]; }
         if (q0 < NT) store(q0, i0, j0, c0);
         if (q1 < NT) store(q1, i1, j1, c1);
     }
@@ -615,7 +624,7 @@ CPDP_D_NOINLINE void bdf_solve(const double c) {
     CPDP_LOOP for (int e = tid; e < NX * NP; e += nt) {                  // B_W + c X C
         const int i = e / NP, k = e % NP;
         double acc = 0.0;
-        CPDP_LOOP for (int a = 0; a < NX; ++a) acc += s.P[i * NX + a] * bs.Cm[a * NP + k];
+        CPDP_MM_LOOP for (int a = 0; a < NX; ++a) acc += s.P[i * NX + a] * bs.Cm[a * NP + k];
         tmp[NT + e] = dW[e] + c * acc;
     }
     CPDP_LOOP for (int k = tid; k < NT; k += nt) dy[k] = tmp[k];
@@ -623,7 +632,7 @@ CPDP_D_NOINLINE void bdf_solve(const double c) {
     CPDP_LOOP for (int e = tid; e < NX * NP; e += nt) {                  // dW = (I + cL)^{-1} (...)
         const int i = e / NP, k = e % NP;
         double acc = 0.0;
-        CPDP_LOOP for (int a = 0; a < NX; ++a) acc += bs.Winv[i * NX + a] * tmp[NT + a * NP + k];
+        CPDP_MM_LOOP for (int a = 0; a < NX; ++a) acc += bs.Winv[i * NX + a] * tmp[NT + a * NP + k];
         dW[e] = acc;
     }
     BDF_SYNC();
