@@ -290,7 +290,7 @@ def run_ours(a):
     clocks = sampler.stop() if rank == 0 else None
     sol_t, aux_t = sol, aux
     # ---- phase times (single stream, each phase alone; explains `value`, is not part of it) -------------------------
-    for _ in range(2):                                    # untimed: allocates the single-stream workspace, warms the caches
+    for _ in range(3):                                    # untimed: allocates the single-stream workspace, warms the caches
         s0 = oc.cocSolverBatch(resident["x0"], 1.0, resident["theta"], pdata=resident["goal"])
         oc.auxSysSolverBatch(s0, resident["taus"], resident["wp"], qb["sel"])
     sync_all()
@@ -316,9 +316,9 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    solve_ms = float(np.mean([p[0].elapsed_time(p[1]) for p in ph]))
-    back_ms = float(np.mean([p[1].elapsed_time(p[2]) for p in ph]))
-    fwd_ms = float(np.mean([p[2].elapsed_time(p[3]) for p in ph]))
+    solve_ms = float(np.median([p[0].elapsed_time(p[1]) for p in ph]))
+    back_ms = float(np.median([p[1].elapsed_time(p[2]) for p in ph]))
+    fwd_ms = float(np.median([p[2].elapsed_time(p[3]) for p in ph]))
     rounds = lib.last_rounds()
 
     # ---- timed region 2: end to end through the public API with HOST buffers ---------------------------------
