@@ -221,10 +221,21 @@ def run_ours(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes to stdout too
+        # stdout carries exactly one JSON line: NCCL prints its "NCCL version ..." banner to stdout while the communicator
+        # is created, so file descriptor 1 points at stderr until that has happened
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     B_total = a.batch * world if a.scaling == "weak" else a.batch
     lo, hi = synthetic.shard_bounds(B_total, world, rank)
     Bl = hi - lo
