@@ -469,6 +469,7 @@ CPDP_D_NOINLINE bool bdf_factor(const double c) {
         bs.Dr[q] = dr / dd; bs.Di[q] = -di / dd;
     }
     bad = bdf_reduce(bad, true);
+    BDF_SYNC();                                      // S, Dr, Di visible to every lane (the one-warp reduction has no barrier of its own)
     if (bad != 0.0) return false;
     CPDP_LOOP for (int e = tid; e < n * n; e += nt) {          // Sr = Re(G^H S G) -> Gr   (real: (I + cL)^{-1} and Q are)
         const int i = e / n, j = e % n;
