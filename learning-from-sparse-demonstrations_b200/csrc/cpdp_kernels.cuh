@@ -362,7 +362,10 @@ CPDP_HD void chol_solve(const double* L, double* b) {
 //  3. IPOPT filter line search (one thread per interval re-integrates the RK4 map).
 //  4. Primal / dual update.
 // ------------------------------------------------------------------------------------------------
-constexpr int NEWTON_THREADS = 64;
+#ifndef CPDP_NEWTON_THREADS
+#define CPDP_NEWTON_THREADS 64
+#endif
+constexpr int NEWTON_THREADS = CPDP_NEWTON_THREADS;
 
 CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
     const int tid = threadIdx.x, nt = blockDim.x;
