@@ -281,8 +281,12 @@ CPDP_D bool schur_real_w0(double* H, double* Z) {
                     p = h_(k, k - 1); q = h_(k + 1, k - 1); r = notlast ? h_(k + 2, k - 1) : 0.0;
                     x2 = fabs(p) + fabs(q) + fabs(r);
                     if (x2 == 0.0) continue;
+#ifdef CPDP_SCHUR_NONORM
+                    x2 = 1.0;          // tuning knob: skip EISPACK's overflow guard (entries of L are O(1e3) at most here)
+#else
                     const double ix2 = 1.0 / x2;
                     p *= ix2; q *= ix2; r *= ix2;
+#endif
                 }
                 double s = sqrt(p * p + q * q + r * r);
                 if (s == 0.0) continue;
