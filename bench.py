@@ -34,8 +34,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="OCPs per GPU (weak scaling) or in total (--scaling strong)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=4096, help="OCPs in total (--scaling strong, BASELINE's configuration) or per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--n-grid", type=int, default=50)
     ap.add_argument("--mode", default=None, choices=["bdf", "rk45"], help="backward Riccati integrator")
     ap.add_argument("--rtol", type=float, default=1e-3)
@@ -253,8 +253,8 @@ def run_ours(a):
     h2d_bytes = sum(v.numel() * 8 for v in host.values())
     resident = {k: v.to(dev) for k, v in host.items()}
     r = oc.n_auxvar
-    gathered = torch.empty((B_total, r + 1), dtype=torch.float64, device=dev)
-    result_host = torch.empty((r + 1,), dtype=torch.float64).pin_memory()
+    gathered = torch.empty((B_total, r + 2), dtype=torch.float64, device=dev)
+    result_host = torch.empty((r + 2,), dtype=torch.float64).pin_memory()
     stats = {}
 
     def step(inp):
@@ -267,13 +267,13 @@ def run_ours(a):
             sol = oc.cocSolverBatch(inp["x0"], 1.0, inp["theta"], pdata=inp["goal"])
             aux = oc.auxSysSolverBatch(sol, inp["taus"], inp["wp"], qb["sel"])
         stats["rounds"] = lib.last_rounds()
-        rows = torch.cat([aux["loss"].unsqueeze(1), aux["dtheta"]], dim=1)
+        rows = oc.packRows(sol, aux)                        # [loss | dL/dtheta | failed] per OCP, packed on the device
         if world > 1:
-            dist.all_gather_into_tensor(gathered, rows)     # the single exchange of the iteration (64 B / OCP)
+            dist.all_gather_into_tensor(gathered, rows)     # the single exchange of the iteration (72 B / OCP)
             allrows = gathered
         else:
             allrows = rows
-        red = oc.reduceBatch(allrows[:, 0].contiguous(), allrows[:, 1:].contiguous())
+        red = oc.reduceRows(allrows)                        # [sum loss | sum dL/dtheta | number of failed OCPs]
         return red, sol, aux
 
     def sync_all():
@@ -313,13 +313,13 @@ def run_ours(a):
         aux = oc.auxSysSolverBatch(sol, resident["taus"], resident["wp"], qb["sel"], phases=1)     # backward kernel alone
         e2.record()
         aux = oc.auxSysSolverBatch(sol, resident["taus"], resident["wp"], qb["sel"], phases=2, out=aux)
-        rows = torch.cat([aux["loss"].unsqueeze(1), aux["dtheta"]], dim=1)
+        rows = oc.packRows(sol, aux)
         if world > 1:
             dist.all_gather_into_tensor(gathered, rows)
             allrows = gathered
         else:
             allrows = rows
-        red = oc.reduceBatch(allrows[:, 0].contiguous(), allrows[:, 1:].contiguous())
+        red = oc.reduceRows(allrows)
         e3.record()
         ph.append((e0, e1, e2, e3))
     sync_all()
@@ -411,7 +411,7 @@ def run_ours(a):
                    "l2": "inputs larger than L2: per-step working set (~%.1f GB workspace + outputs) exceeds the 126 MB L2, "
                          "every step starts from the zero seed" % (lib.workspace_bytes(Bl, a.n_grid, 4) / 1e9)},
         "e2e": {"value": B_total * a.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": (r + 1) * 8},
+                "d2h_bytes_per_step": (r + 2) * 8},
         # timed region: per chunk k_solve_init + k_compact + 4 kernels per Newton round + backward + forward sweep, then one
         # k_reduce_tree (single-stream mode launches only the rounds the adaptive solve needed)
         "gpu_launches": a.steps * ((a.chunks * (2 + 4 * a.rounds + 2) + 1) if a.chunks > 1 else (2 + 4 * rounds + 2 + 1)),

@@ -7,9 +7,12 @@
  *
  * Conventions: all arrays are row-major IEEE fp64 DEVICE pointers owned by the caller unless marked (host);
  * n = states, m = controls, r = learnable parameters (cpdp_model_dims), B problems, N grid intervals,
- * S RK4 sub-steps per interval.  Calls are stream-ordered on `stream` (a cudaStream_t passed as void*), hold no
- * state between calls, and return 0, a negative argument-error code or a positive cudaError_t
- * (cpdp_error_string).  Numerical outcomes are reported per problem in status arrays, never as return codes.
+ * S RK4 sub-steps per interval.  Calls are stream-ordered on `stream` (a cudaStream_t passed as void*) and return 0, a
+ * negative argument-error code or a positive cudaError_t (cpdp_error_string).  The library keeps no device state between
+ * calls (everything lives in caller-owned buffers) and no host state shared between threads: the only host variables are
+ * thread-local (the launch error of the call in progress, and the round count behind cpdp_last_rounds), so host threads
+ * driving different streams or devices do not interfere.  Numerical outcomes are reported per problem in status arrays,
+ * never as return codes.
  */
 #ifndef CPDP_H
 #define CPDP_H
@@ -38,7 +41,7 @@ size_t cpdp_workspace_bytes(int B, int N, int S);
 /* Replaces COCSys.cocSolver (CPDP.py:92-198) for B problems: RK4 multiple-shooting NLP, all-zeros seed,
  * Newton-KKT with IPOPT's inertia correction and filter line search.
  *   x0[B][n]; theta[B][r] (theta_stride = r) or shared theta[r] (theta_stride = 0); T horizon;
- *   tol: KKT tolerance; max_iter: Newton iteration cap;
+ *   tol: KKT tolerance; max_iter: Newton iteration cap, 0..255 (the per-problem filter holds 256 corners; -10 otherwise);
  *   rounds > 0: launch exactly that many Newton rounds with no host synchronisation (CUDA-graph capturable);
  *   rounds = 0: poll the number of unconverged problems (one stream sync per round) and stop early.
  * Outputs X[B][N+1][n], U[B][N+1][m] (row N copies row N-1, CPDP.py:191), Lam[B][N+1][n] (= lam_g, CPDP.py:193),
@@ -49,7 +52,7 @@ int cpdp_solve(void* ws, size_t ws_bytes, int B, int N, int S, double T,
                double* X, double* U, double* Lam, int* status, int* iters,
                double* kkt_out, double* cost_out, void* stream);
 
-/* Newton rounds launched by the most recent cpdp_solve of this process (4 kernel launches per round + 2). */
+/* Newton rounds launched by the most recent cpdp_solve of the calling thread (4 kernel launches per round + 2). */
 int cpdp_last_rounds(void);
 
 /* Replaces COCSys.auxSysSolver (CPDP.py:301-381) and the getloss_*corrections closures
@@ -61,7 +64,8 @@ int cpdp_last_rounds(void);
  *   taus[W] (stride 0); wp[B][W][D].  W = 0 skips the loss.
  * Outputs Xa[B][N+1][n*r] (dx/dtheta nodes), Ua[B][N+1][m*r], loss[B], dtheta[B][r] (reference convention:
  * dl_dy = y - wp, i.e. half the true gradient), aux_status[B] (0 ok, 1 step too small, 2 non-finite, 3 skipped
- * because the forward solve produced no trajectory, 4 singular Newton matrix), counters[B][cpdp_num_counters()=6]
+ * because the forward solve produced no trajectory, 4 singular Newton matrix, 5 a waypoint time outside [0, T] -- scipy's
+ * interp1d raises there in the reference), counters[B][cpdp_num_counters()=6]
  * (backward rhs evals, backward steps, forward rhs evals, forward steps, backward LU factorisations, backward
  * Jacobian evaluations). */
 int cpdp_aux(void* ws, size_t ws_bytes, int B, int N, int S, double T,
@@ -87,6 +91,35 @@ int cpdp_dfma_probe(double* sink, int blocks, int iters, void* stream);
 /* Cross-problem sum of [loss | dL/dtheta] rows in a fixed binary tree over the row index (bit-identical for any
  * sharding of the rows over GPUs once they are all-gathered).  scratch: nextpow2(B)*(1+r) doubles; out[1+r]. */
 int cpdp_reduce(const double* loss, const double* dtheta, int B, double* scratch, double* out, void* stream);
+
+/* Rows [loss | dL/dtheta | bad] (r + 2 doubles per problem): the unit of the one cross-GPU exchange of an iteration
+ * (all-gather) -- bad = 1 when the problem's forward solve did not end CPDP_CONVERGED (solve_status may be NULL) or its
+ * aux_status != 0, so that failures travel with the sum instead of disappearing into it (the reference never looks at
+ * IPOPT's status, CPDP.py:183).  rows[B][r+2]. */
+int cpdp_pack_rows(const double* loss, const double* dtheta, const int* solve_status, const int* aux_status, int B,
+                   double* rows, void* stream);
+
+/* Fixed binary-tree sum over the row index of B rows of C doubles (same tree as cpdp_reduce; bit-identical for any
+ * sharding of the rows).  With cpdp_pack_rows rows: out = [sum loss | sum dL/dtheta | number of failed problems].
+ * scratch: nextpow2(B)*C doubles; out[C]. */
+int cpdp_reduce_rows(const double* rows, int B, int C, double* scratch, double* out, void* stream);
+
+/* Learner step on the device: replaces the update rules, projection and stop rule of lib/QuadAlgorithm.py:239-257,
+ * 454-578 so that a learning run is a stream of launches (CUDA-graph capturable).
+ *   phase 0: theta_eval[r] <- evaluation point of the next gradient iteration (theta + mu*velocity for Nesterov,
+ *            QuadAlgorithm.py:480; theta otherwise; theta when defer_close = 1, the second evaluation of
+ *            true_loss_print_flag).
+ *   phase 1: update theta from red = [loss | dL/dtheta | ...] in the reference's numpy association, theta[0] =
+ *            max(theta[0], 1e-8), param_trace[it+1] = theta, loss_trace[it] = loss, it[0] += 1, it[1] = 1 (stop) unless
+ *            loss > loss_stop and |dL| > grad_stop.  defer_close = 1 leaves the iteration open for a phase-2 call.
+ *   phase 2: record loss / apply the stop rule with a second evaluation at the updated theta (QuadAlgorithm.py:490-492).
+ *   method: 0 Vanilla, 1 Nesterov, 2 Adam, 3 Nadam, 4 AMSGrad.  Once it[1] != 0 (or it[0] == cap) phases 1/2 do nothing.
+ *   theta[r], theta_eval[r], state[3][r] (zeroed by the caller), it[2] (zeroed), loss_trace[cap],
+ *   param_trace[cap+1][r] (row 0 = initial theta, written by the caller): all device memory. */
+int cpdp_optim_step(int phase, int method, double lr, double mu, double beta1, double beta2, double eps,
+                    double loss_stop, double grad_stop, double* theta, double* theta_eval, double* state,
+                    const double* red, int* it, double* loss_trace, double* param_trace, int cap, int defer_close,
+                    void* stream);
 
 const char* cpdp_error_string(int code);
 

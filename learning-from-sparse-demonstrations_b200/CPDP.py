@@ -60,6 +60,7 @@ class _Interp:
     def __init__(self, x, y, method=1):
         self.time_grid = numpy.asarray(x, dtype=float)
         self.nodes = numpy.asarray(y, dtype=float)
+        self.method = method
         self._f = ip.interp1d(self.time_grid, self.nodes, axis=0) if method == 1 else \
             ip.interp1d(self.time_grid, self.nodes, axis=0, kind='cubic')
 
@@ -340,10 +341,37 @@ class COCSys:
         lib.reduce(mem.ptr(loss), mem.ptr(dtheta), B, mem.ptr(scratch), mem.ptr(out), mem.stream())
         return out
 
+    def packRows(self, sol, aux):
+        """Device rows [B, r+2] = [loss | dL/dtheta | bad] (bad = 1: forward solve not converged or a sweep failed); the
+        unit of the cross-GPU all-gather."""
+        lib = self.build()
+        mem = self._device()
+        B = int(aux["loss"].shape[0])
+        rows = mem.empty((B, self.n_auxvar + 2))
+        lib.pack_rows(mem.ptr(aux["loss"]), mem.ptr(aux["dtheta"]), mem.ptr(sol.get("status")), mem.ptr(aux["aux_status"]), B,
+                      mem.ptr(rows), mem.stream())
+        return rows
+
+    def reduceRows(self, rows):
+        """Fixed-tree sum of packRows rows: device array [r+2] = [sum loss | sum dL/dtheta | number of failed OCPs]."""
+        lib = self.build()
+        mem = self._device()
+        B, C = int(rows.shape[0]), int(rows.shape[1])
+        p2 = 1
+        while p2 < B:
+            p2 *= 2
+        scratch = mem.empty((p2 * C,))
+        out = mem.empty((C,))
+        lib.reduce_rows(mem.ptr(rows), B, C, mem.ptr(scratch), mem.ptr(out), mem.stream())
+        return out
+
     def gradIterBatch(self, ini_states, horizon, auxvar_value, taus, waypoints, sel, pdata=None, mode=None, rounds=0,
                       chunks=1):
         """One CPDP gradient iteration for a batch: forward solve, auxiliary system, loss and dL/dtheta, and their
-        fixed-order sums.  Returns (sum_loss_and_grad [1+r] device array, sol dict, aux dict).
+        fixed-order sums.  Returns (sum_loss_and_grad [1+r] device array, sol dict, aux dict).  ``aux["n_failed"]`` is a
+        one-element device array (no host synchronisation): the number of OCPs whose forward solve did not end `converged`
+        (incl. still iterating after a fixed number of ``rounds``) or whose sweeps failed -- their rows may be zero, so a
+        caller must not step on the sum when it is non-zero (``optim.cpdp_grad_fn`` raises).
 
         chunks > 1 (needs rounds > 0, i.e. no host synchronisation inside the solve): the batch is cut into that many
         contiguous chunks, each running solve -> backward sweep -> forward sweep on its own CUDA stream with its own
@@ -354,8 +382,9 @@ class COCSys:
         if chunks <= 1 or not hasattr(mem, "torch"):
             sol = self.cocSolverBatch(ini_states, horizon, auxvar_value, pdata=pdata, rounds=rounds)
             aux = self.auxSysSolverBatch(sol, taus, waypoints, sel, mode=mode)
-            red = self.reduceBatch(aux["loss"], aux["dtheta"])
-            return red, sol, aux
+            full = self.reduceRows(self.packRows(sol, aux))
+            aux["n_failed"] = full[1 + self.n_auxvar:]
+            return full[:1 + self.n_auxvar], sol, aux
         assert rounds > 0, "chunks > 1 needs a fixed number of Newton rounds (rounds > 0): the adaptive mode blocks the host"
         torch = mem.torch
         x0 = mem.from_host(numpy.asarray(ini_states, dtype=float).reshape(-1, self.n_state)
@@ -390,8 +419,9 @@ class COCSys:
         sol = {k: torch.cat([s_[k] for s_ in sols]) for k in ("X", "U", "Lam", "status", "iters", "kkt", "cost")}
         sol.update(time_grid=sols[0]["time_grid"], horizon=float(horizon), B=B, chunks=sols)
         aux = {k: torch.cat([a_[k] for a_ in auxs]) for k in ("Xa", "Ua", "loss", "dtheta", "aux_status", "counters")}
-        red = self.reduceBatch(aux["loss"], aux["dtheta"])
-        return red, sol, aux
+        full = self.reduceRows(self.packRows(sol, aux))
+        aux["n_failed"] = full[1 + self.n_auxvar:]
+        return full[:1 + self.n_auxvar], sol, aux
 
     # ------------------------------------------------------------------ reference-shaped single-problem API
     def cocSolver(self, ini_state, horizon, auxvar_value=1, interplation_level=1, print_level=0):
@@ -426,6 +456,12 @@ class COCSys:
         time_grid = numpy.asarray(time_grid, dtype=float)
         N = time_grid.size - 1
         assert N == self.n_grid, "time_grid does not match setIntegrator(n_grid)"
+        # the sweeps integrate the LINEAR interpolant of the node table on the uniform grid cocSolver returns (CPDP.py:192,386)
+        if getattr(opt_sol, 'method', 1) != 1:
+            raise NotImplementedError("auxSysSolver integrates the linear interpolant (interplation_level=1, the level every "
+                                      "reference script uses); a cubic opt_sol is not supported")
+        if not numpy.allclose(time_grid, numpy.linspace(0.0, time_grid[-1], N + 1), rtol=0, atol=1e-12 * max(1.0, abs(time_grid[-1]))):
+            raise NotImplementedError("auxSysSolver needs the uniform time grid returned by cocSolver")
         th, th_stride = self._theta_arg(numpy.atleast_1d(numpy.asarray(auxvar_value, dtype=float)), 1)
         pd = getattr(self, 'pdata_value', None)
         sol = dict(B=1, horizon=float(time_grid[-1]), theta=th, theta_stride=th_stride,

@@ -110,6 +110,12 @@ class CpdpLib:
         L.cpdp_dfma_probe.restype = _i
         L.cpdp_reduce.argtypes = [_vp, _vp, _i, _vp, _vp, _vp]
         L.cpdp_reduce.restype = _i
+        L.cpdp_pack_rows.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _vp]
+        L.cpdp_pack_rows.restype = _i
+        L.cpdp_reduce_rows.argtypes = [_vp, _i, _i, _vp, _vp, _vp]
+        L.cpdp_reduce_rows.restype = _i
+        L.cpdp_optim_step.argtypes = [_i, _i, _d, _d, _d, _d, _d, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]
+        L.cpdp_optim_step.restype = _i
         if hasattr(L, "cpdp_error_string"):
             L.cpdp_error_string.argtypes = [_i]
             L.cpdp_error_string.restype = ctypes.c_char_p
@@ -152,6 +158,17 @@ class CpdpLib:
 
     def dfma_probe(self, sink, blocks, iters, stream):
         self.check(self.L.cpdp_dfma_probe(sink, blocks, iters, stream), "cpdp_dfma_probe")
+
+    def pack_rows(self, loss, dtheta, solve_status, aux_status, B, rows, stream):
+        self.check(self.L.cpdp_pack_rows(loss, dtheta, solve_status, aux_status, B, rows, stream), "cpdp_pack_rows")
+
+    def reduce_rows(self, rows, B, C, scratch, out, stream):
+        self.check(self.L.cpdp_reduce_rows(rows, B, C, scratch, out, stream), "cpdp_reduce_rows")
+
+    def optim_step(self, phase, method, lr, mu, beta1, beta2, eps, loss_stop, grad_stop, theta, theta_eval, state, red, it,
+                   loss_trace, param_trace, cap, defer_close, stream):
+        self.check(self.L.cpdp_optim_step(phase, method, lr, mu, beta1, beta2, eps, loss_stop, grad_stop, theta, theta_eval,
+                                          state, red, it, loss_trace, param_trace, cap, defer_close, stream), "cpdp_optim_step")
 
     def reduce(self, loss, dtheta, B, scratch, out, stream):
         self.check(self.L.cpdp_reduce(loss, dtheta, B, scratch, out, stream), "cpdp_reduce")

@@ -99,6 +99,10 @@ def generate_model_header(name, state, control, auxvar, dyn, path_cost, final_co
     pdv = _vec(pdata) if pdata is not None else []
     n, m, r = len(x), len(u), len(th)
     nq = len(pdv)
+    # sx.SX.sym is backed by sympy symbols, which are identified by NAME (CasADi's are distinct objects): a name reused across
+    # state / control / auxvar / problem constants would silently alias two variables
+    allsyms = x + u + th + pdv
+    assert len(set(allsyms)) == len(allsyms), "state, control, auxvar and problem variables must have distinct symbol names"
     nz = n + m
     f = sp.Matrix(_vec(dyn))
     c = _to_matrix(path_cost)[0, 0]

@@ -60,11 +60,11 @@ static WsLayout ws_carve(char* base, int B, int N, int S) {
 
 }  // namespace CPDP_NS
 
-static int g_last_rounds = 0;
+static thread_local int g_last_rounds = 0;
 
 extern "C" {
 
-// Newton rounds launched by the most recent cpdp_solve call of this process (each round = 4 kernel launches).
+// Newton rounds launched by the most recent cpdp_solve call of the CALLING THREAD (each round = 4 kernel launches).
 CPDP_API int cpdp_last_rounds(void) { return g_last_rounds; }
 
 CPDP_API int cpdp_model_dims(int* n, int* m, int* r, int* q) {
@@ -99,7 +99,8 @@ CPDP_API int cpdp_solve(void* ws, size_t ws_bytes, int B, int N, int S, double T
     WsLayout w = ws_carve((char*)ws, B, N, S);
     if (w.bytes > ws_bytes) return -3;
     SolveArgs a = w.sa;
-    a.B = B; a.N = N; a.S = S; a.T = T; a.tol = tol; a.max_iter = (max_iter < FILTER_CAP) ? max_iter : FILTER_CAP - 1;
+    if (max_iter < 0 || max_iter >= FILTER_CAP) return -10;      // the per-problem filter holds FILTER_CAP corners (one per iteration at most)
+    a.B = B; a.N = N; a.S = S; a.T = T; a.tol = tol; a.max_iter = max_iter;
     if (NQ > 0 && !pdata) return -8;
     a.x0 = x0; a.theta = theta; a.theta_stride = theta_stride; a.pdata = pdata;
     a.X = X; a.U = U; a.Lam = Lam; a.status = status; a.iters = iters;
@@ -210,6 +211,49 @@ CPDP_API int cpdp_reduce(const double* loss, const double* dtheta, int B, double
     using namespace CPDP_NS;
     if (!loss || !dtheta || !out || !scratch || B <= 0) return -1;
     CPDP_LAUNCH(k_reduce_tree, 1, 256, 0, (cudaStream_t)stream, loss, dtheta, B, scratch, out);
+    return CPDP_LAST_ERROR();
+}
+
+// Rows [loss | dL/dtheta | bad] (r + 2 doubles per problem) for the cross-GPU all-gather; bad = 1 when the forward solve of
+// the problem did not converge (solve_status != converged; may be null) or an auxiliary sweep failed (aux_status != 0).
+CPDP_API int cpdp_pack_rows(const double* loss, const double* dtheta, const int* solve_status, const int* aux_status, int B,
+                            double* rows, void* stream) {
+    using namespace CPDP_NS;
+    if (!loss || !dtheta || !rows || B <= 0) return -1;
+    const int grid = (int)(((size_t)B * (NP + 2) + 255) / 256);
+    CPDP_LAUNCH(k_pack_rows, grid < 1024 ? grid : 1024, 256, 0, (cudaStream_t)stream, loss, dtheta, solve_status, aux_status, B, rows);
+    return CPDP_LAST_ERROR();
+}
+
+// Fixed binary-tree sum (over the row index) of B rows of C doubles -> out[C]; scratch: nextpow2(B)*C doubles.  With the rows
+// of cpdp_pack_rows: out = [sum loss | sum dL/dtheta | number of failed problems].
+CPDP_API int cpdp_reduce_rows(const double* rows, int B, int C, double* scratch, double* out, void* stream) {
+    using namespace CPDP_NS;
+    if (!rows || !out || !scratch || B <= 0 || C <= 0) return -1;
+    CPDP_LAUNCH(k_reduce_rows, 1, 256, 0, (cudaStream_t)stream, rows, B, C, scratch, out);
+    return CPDP_LAST_ERROR();
+}
+
+// Learner step on the device (lib/QuadAlgorithm.py:239-257, 454-578).  phase 0: theta_eval <- evaluation point of the next
+// gradient iteration (theta + mu*velocity for Nesterov, theta otherwise).  phase 1: update from red = [loss | dL/dtheta | ..],
+// projection theta[0] >= 1e-8, traces, stop rule.  phase 2: Nesterov's true_loss_print_flag second evaluation (records loss
+// and applies the stop rule with the gradient at the new point; no update).  With phase 1 followed by phase 2 pass
+// defer_close = 1 to phase 1.  method: 0 Vanilla, 1 Nesterov, 2 Adam, 3 Nadam, 4 AMSGrad.
+// state[3][r] zero-initialised by the caller; it[2] = {iterations done, stop flag} zero-initialised; param_trace row 0 = theta0.
+CPDP_API int cpdp_optim_step(int phase, int method, double lr, double mu, double beta1, double beta2, double eps,
+                             double loss_stop, double grad_stop, double* theta, double* theta_eval, double* state,
+                             const double* red, int* it, double* loss_trace, double* param_trace, int cap, int defer_close,
+                             void* stream) {
+    using namespace CPDP_NS;
+    if (!theta || !theta_eval || !state || !it || phase < 0 || phase > 2 || method < 0 || method > 4) return -1;
+    if (phase > 0 && (!red || !loss_trace || !param_trace || cap <= 0)) return -1;
+    OptimArgs a;
+    a.method = method; a.lr = lr; a.mu = mu; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+    a.loss_stop = loss_stop; a.grad_stop = grad_stop;
+    a.theta = theta; a.theta_eval = theta_eval; a.state = state; a.red = red; a.it = it;
+    a.loss_trace = loss_trace; a.param_trace = param_trace; a.cap = cap;
+    if (phase == 0) { a.record_only = defer_close ? 1 : 0; CPDP_LAUNCH(k_optim_pre, 1, 32, 0, (cudaStream_t)stream, a); }
+    else { a.record_only = (phase == 2) ? 1 : (defer_close ? -1 : 0); CPDP_LAUNCH(k_optim_post, 1, 32, 0, (cudaStream_t)stream, a); }
     return CPDP_LAST_ERROR();
 }
 

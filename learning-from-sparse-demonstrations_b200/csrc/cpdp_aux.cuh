@@ -645,12 +645,16 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_aux_forward(AuxArgs a) {
         __syncthreads();
     }
     if (tid == 0) { a.aux_status[b] = st; a.counters[b * NCOUNTERS + 2] = nrhs; a.counters[b * NCOUNTERS + 3] = nsteps; }
-    // ---- loss and gradient (thread i < NP accumulates dL[i]; thread 0 the loss)
+    // ---- loss and gradient: thread 0 the loss, parameter i by thread i % nt (strided: r may exceed the CTA size).
+    //      A waypoint time outside [0, T] is an error (scipy's interp1d raises ValueError in the reference): status 5.
     const double* taus = a.taus + (size_t)b * a.taus_stride;
     const double* wp = a.wp + (size_t)b * a.W * a.D;
-    if (tid < NP || tid == 0) {
-        double acc = 0.0, lo_ = 0.0;
-        for (int w = 0; w < a.W; ++w) {
+    bool tau_bad = false;
+    for (int w = 0; w < a.W; ++w) if (!(taus[w] >= 0.0 && taus[w] <= p.dt * N)) tau_bad = true;
+    if (tau_bad && st == 0) { st = 5; if (tid == 0) a.aux_status[b] = 5; }
+    if (tid == 0) {
+        double lo_ = 0.0;
+        for (int w = 0; w < a.W && st == 0; ++w) {
             const double t = taus[w];
             const int lo = interp_lo(t, p.dt, N);
             const double xlo = p.dt * lo, xhi = p.dt * (lo + 1);
@@ -658,16 +662,26 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_aux_forward(AuxArgs a) {
                 const int si = a.sel[d];
                 const double yv = interp_val(p.X[(size_t)lo * NX + si], p.X[(size_t)(lo + 1) * NX + si], xlo, xhi, t);
                 const double diff = yv - wp[(size_t)w * a.D + d];
-                if (tid == 0) lo_ += diff * diff;
-                if (tid < NP) {
-                    const double xa = interp_val(Xa[(size_t)lo * NYF + si * NP + tid], Xa[(size_t)(lo + 1) * NYF + si * NP + tid], xlo, xhi, t);
-                    acc += diff * xa;
-                }
+                lo_ += diff * diff;
             }
         }
-        if (st != 0) { acc = 0.0; lo_ = 0.0; }
-        if (tid < NP) a.dtheta[(size_t)b * NP + tid] = acc;
-        if (tid == 0) a.loss[b] = lo_;
+        a.loss[b] = lo_;
+    }
+    for (int i = tid; i < NP; i += nt) {
+        double acc = 0.0;
+        for (int w = 0; w < a.W && st == 0; ++w) {
+            const double t = taus[w];
+            const int lo = interp_lo(t, p.dt, N);
+            const double xlo = p.dt * lo, xhi = p.dt * (lo + 1);
+            for (int d = 0; d < a.D; ++d) {
+                const int si = a.sel[d];
+                const double yv = interp_val(p.X[(size_t)lo * NX + si], p.X[(size_t)(lo + 1) * NX + si], xlo, xhi, t);
+                const double diff = yv - wp[(size_t)w * a.D + d];
+                const double xa = interp_val(Xa[(size_t)lo * NYF + si * NP + i], Xa[(size_t)(lo + 1) * NYF + si * NP + i], xlo, xhi, t);
+                acc += diff * xa;
+            }
+        }
+        a.dtheta[(size_t)b * NP + i] = acc;
     }
 }
 

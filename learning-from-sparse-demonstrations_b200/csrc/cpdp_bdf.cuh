@@ -694,20 +694,34 @@ CPDP_D_NOINLINE double bdf_norm(const double* v, const double* scale, const doub
     return sqrt(bdf_reduce(a, false) / (double)NFULL_R);
 }
 
+// Developer instrumentation (-DCPDP_BDF_TIMING): per-phase clock64() totals of each problem, written over the Ua rows of
+// the problem at kernel end (phases = 1 runs only; tools/prof_bdf_phases.py).  Off in the shipped library.
+#ifdef CPDP_BDF_TIMING
+#define BDF_T(ph, expr) do { const long long t0__ = clock64(); expr; tp[ph] += clock64() - t0__; } while (0)
+#define BDF_TB(ph, var, expr) do { const long long t0__ = clock64(); var = (expr); tp[ph] += clock64() - t0__; } while (0)
+#define BDF_TP_PARAM , long long* tp
+#define BDF_TP_ARG , tp
+#else
+#define BDF_T(ph, expr) do { expr; } while (0)
+#define BDF_TB(ph, var, expr) do { var = (expr); } while (0)
+#define BDF_TP_PARAM
+#define BDF_TP_ARG
+#endif
+
 // One grid interval [t0, t1] with scipy's BDF.  y in/out (shared memory).  Returns 0 ok, 1 step too small,
 // 2 non-finite, 4 singular Newton matrix.  cnt: [rhs evaluations, steps (accepted), LU factorisations, Jacobians]
 CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProblem& p, const double t0, const double t1,
-                        const double rtol, const double atol, double* y, double* tms, int* cnt) {
+                        const double rtol, const double atol, double* y, double* tms, int* cnt BDF_TP_PARAM) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const double dir = (t1 >= t0) ? 1.0 : -1.0;
     const double EPS = 2.220446049250313e-16;
     // ---- __init__ (bdf.py:200-257)
     if (tid == 0) tms[0] = t0;
-    if (!bdf_prepare(p, s.M)) return 2;
+    { bool okp__; BDF_TB(0, okp__, bdf_prepare(p, s.M)); if (!okp__) return 2; }
     double* f0 = bs.d;                 // f(t0, y0) parked in the (not yet used) d row
-    bdf_rhs(s.M, y, f0); ++cnt[0];
-    bdf_jacobian(s.M, y); ++cnt[3];
-    if (!bdf_schur()) return 4;
+    BDF_T(1, bdf_rhs(s.M, y, f0)); ++cnt[0];
+    BDF_T(2, bdf_jacobian(s.M, y)); ++cnt[3];
+    { bool oks__; BDF_TB(3, oks__, bdf_schur()); if (!oks__) return 4; }
     double h_abs;
     {
         const double interval_length = fabs(t1 - t0);
@@ -723,8 +737,8 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
         h0 = fmin(h0, interval_length);
         CPDP_LOOP for (int i = tid; i < NYR; i += nt) bs.dy[i] = y[i] + h0 * dir * f0[i];
         if (tid == 0) tms[0] = t0 + h0 * dir;
-        if (!bdf_prepare(p, s.M)) return 2;
-        bdf_rhs(s.M, bs.dy, bs.tmp); ++cnt[0];
+        { bool okp__; BDF_TB(0, okp__, bdf_prepare(p, s.M)); if (!okp__) return 2; }
+        BDF_T(1, bdf_rhs(s.M, bs.dy, bs.tmp)); ++cnt[0];
         double a2 = 0.0;
         CPDP_LOOP for (int i = tid; i < NYR; i += nt) {
             const double sc = atol + fabs(y[i]) * rtol;
@@ -749,7 +763,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
         // ---- _step_impl (bdf.py:314-453)
         const double min_step = 10 * fabs(nextafter(t, dir * INFINITY) - t);
         if (h_abs < min_step) {
-            bdf_change_D(bs.D, order, min_step / h_abs);
+            BDF_T(7, bdf_change_D(bs.D, order, min_step / h_abs));
             h_abs = min_step;
             n_equal_steps = 0;
         }
@@ -762,7 +776,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
             t_new = t + h;
             if (dir * (t_new - t1) > 0) {
                 t_new = t1;
-                bdf_change_D(bs.D, order, fabs(t_new - t) / h_abs);
+                BDF_T(7, bdf_change_D(bs.D, order, fabs(t_new - t) / h_abs));
                 n_equal_steps = 0;
                 lu_valid = false;
             }
@@ -784,12 +798,12 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                 bs.psi[i] = ps / al;
             }
             if (tid == 0) tms[0] = t_new;
-            if (!bdf_prepare(p, s.M)) return 2;      // PMP matrices at t_new (every Newton iterate shares them)
+            { bool okp__; BDF_TB(0, okp__, bdf_prepare(p, s.M)); if (!okp__) return 2; }      // PMP matrices at t_new (every Newton iterate shares them)
             const double c = h / al;
             bool converged = false;
             while (!converged) {
                 if (!lu_valid) {
-                    if (!bdf_factor(c)) return 4;
+                    { bool okf__; BDF_TB(4, okf__, bdf_factor(c)); if (!okf__) return 4; }
                     lu_valid = true; c_lu = c; ++cnt[2];
                 }
                 // ---- solve_bdf_system (bdf.py:36-75)
@@ -798,7 +812,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                 double dy_norm_old = -1.0;
                 int k = 0;
                 CPDP_LOOP for (k = 0; k < BDF_NEWTON_MAXITER; ++k) {
-                    bdf_rhs(s.M, bs.y, bs.dy); ++cnt[0];
+                    BDF_T(1, bdf_rhs(s.M, bs.y, bs.dy)); ++cnt[0];
                     double fin = 0.0;
                     CPDP_LOOP for (int i = tid; i < NYR; i += nt) {
                         const double fv = bs.dy[i];
@@ -807,8 +821,8 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                     }
                     fin = bdf_reduce(fin, true);
                     if (fin != 0.0) break;
-                    bdf_solve(c_lu);
-                    const double dy_norm = bdf_norm(bs.dy, bs.scale, 1.0);
+                    BDF_T(5, bdf_solve(c_lu));
+                    double dy_norm; BDF_TB(6, dy_norm, bdf_norm(bs.dy, bs.scale, 1.0));
                     const bool have_rate = dy_norm_old >= 0.0;
                     const double rate = have_rate ? dy_norm / dy_norm_old : 0.0;
                     if (have_rate && (rate >= 1 || bdf_pow(rate, (double)(BDF_NEWTON_MAXITER - k)) / (1 - rate) * dy_norm > newton_tol)) break;
@@ -826,15 +840,15 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
                         CPDP_LOOP for (int k = 0; k <= order; ++k) yp += bs.D[(size_t)k * NYR + i];
                         bs.y[i] = yp;
                     }
-                    bdf_jacobian(s.M, bs.y); ++cnt[3];
-                    if (!bdf_schur()) return 4;
+                    BDF_T(2, bdf_jacobian(s.M, bs.y)); ++cnt[3];
+                    { bool oks__; BDF_TB(3, oks__, bdf_schur()); if (!oks__) return 4; }
                     lu_valid = false;
                     current_jac = true;
                 }
             }
             if (!converged) {
                 h_abs *= 0.5;
-                bdf_change_D(bs.D, order, 0.5);
+                BDF_T(7, bdf_change_D(bs.D, order, 0.5));
                 n_equal_steps = 0;
                 lu_valid = false;
                 continue;
@@ -842,12 +856,12 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
             safety = 0.9 * (2 * BDF_NEWTON_MAXITER + 1) / (double)(2 * BDF_NEWTON_MAXITER + n_iter);
             CPDP_LOOP for (int i = tid; i < NYR; i += nt) bs.scale[i] = atol + rtol * fabs(bs.y[i]);
             BDF_SYNC();
-            error_norm = bdf_norm(bs.d, bs.scale, bdf_error_const(order));
+            BDF_TB(6, error_norm, bdf_norm(bs.d, bs.scale, bdf_error_const(order)));
             if (!(error_norm == error_norm)) return 2;
             if (error_norm > 1) {
                 const double factor = fmax(0.2, safety * bdf_pow(error_norm, -1.0 / (order + 1)));
                 h_abs *= factor;
-                bdf_change_D(bs.D, order, factor);
+                BDF_T(7, bdf_change_D(bs.D, order, factor));
                 n_equal_steps = 0;
                 // LU deliberately kept (bdf.py:404-405)
             } else {
@@ -867,8 +881,8 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
         BDF_SYNC();
         if (n_equal_steps < order + 1) continue;
         double error_m_norm = INFINITY, error_p_norm = INFINITY;
-        if (order > 1) error_m_norm = bdf_norm(bs.D + (size_t)order * NYR, bs.scale, bdf_error_const(order - 1));
-        if (order < BDF_MAX_ORDER) error_p_norm = bdf_norm(bs.D + (size_t)(order + 2) * NYR, bs.scale, bdf_error_const(order + 1));
+        if (order > 1) BDF_TB(6, error_m_norm, bdf_norm(bs.D + (size_t)order * NYR, bs.scale, bdf_error_const(order - 1)));
+        if (order < BDF_MAX_ORDER) BDF_TB(6, error_p_norm, bdf_norm(bs.D + (size_t)(order + 2) * NYR, bs.scale, bdf_error_const(order + 1)));
         const double fm = bdf_pow(error_m_norm, -1.0 / order);
         const double f0 = bdf_pow(error_norm, -1.0 / (order + 1));
         const double fp = bdf_pow(error_p_norm, -1.0 / (order + 2));
@@ -878,7 +892,7 @@ CPDP_D int bdf_interval(const AuxShared& s, const BdfShared& bs, const AuxProble
         order += delta_order;
         const double factor = fmin(10.0, safety * fmaxv);
         h_abs *= factor;
-        bdf_change_D(bs.D, order, factor);
+        BDF_T(7, bdf_change_D(bs.D, order, factor));
         n_equal_steps = 0;
         lu_valid = false;
     }
@@ -931,8 +945,12 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, CPDP_BDF_MINB) k_riccati_bdf(Aux
     BDF_SYNC();
     int cnt[4] = {0, 0, 0, 0};
     int st = 0;
+#ifdef CPDP_BDF_TIMING
+    long long tp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tstart__ = clock64();
+#endif
     CPDP_LOOP for (int k = N; k >= 1 && st == 0; --k) {
-        st = bdf_interval(s, bs, p, p.dt * k, p.dt * (k - 1), a.rtol_b, a.atol_b, y, tms, cnt);
+        st = bdf_interval(s, bs, p, p.dt * k, p.dt * (k - 1), a.rtol_b, a.atol_b, y, tms, cnt BDF_TP_ARG);
         CPDP_LOOP for (int q = tid; q < NYR; q += nt) PW[(size_t)(k - 1) * NYR + q] = y[q];
         BDF_SYNC();
     }
@@ -944,6 +962,13 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, CPDP_BDF_MINB) k_riccati_bdf(Aux
             dst[3 * NX * NX + i] = bs.Zr[i]; dst[4 * NX * NX + i] = bs.Zi[i];
         }
         if (tid == 0) dst[5 * NX * NX] = (double)bs.flag[0];
+    }
+#endif
+#ifdef CPDP_BDF_TIMING
+    if (tid == 0) {
+        tp[8] = clock64() - tstart__;
+        double* dst = a.Ua + (size_t)b * (N + 1) * NU * NP;
+        for (int i = 0; i < 10; ++i) dst[i] = (double)tp[i];
     }
 #endif
     if (tid == 0) {

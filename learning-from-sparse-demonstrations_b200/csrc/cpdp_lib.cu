@@ -9,17 +9,17 @@
 #include "cpdp_kernels.cuh"
 #include "cpdp_aux.cuh"
 #include "cpdp_bdf.cuh"
+#include "cpdp_optim.cuh"
 
-static int g_last_error = 0;
-static int g_sms = 0;
+// The only host-side state of the library: the first launch error of the call in progress.  Thread-local, cleared by every
+// entry point before it returns, so host threads driving different streams (or devices) never see each other's errors.
+static thread_local int g_last_error = 0;
 
 static int cpdp_num_sms() {
-    if (g_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sms <= 0) g_sms = 148;
-    }
-    return g_sms;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    return sms;
 }
 
 static int cpdp_take_error() {
@@ -74,6 +74,7 @@ extern "C" CPDP_API const char* cpdp_error_string(int code) {
             case -7: return "unknown integrator mode";
             case -8: return "model has per-problem constants but pdata is null";
             case -9: return "phases must be 1, 2 or 3";
+            case -10: return "max_iter must be in [0, 255]";
             default: return "invalid argument";
         }
     }

@@ -132,8 +132,99 @@ def cpdp_grad_fn(oc, ini_states, horizon, taus, waypoints, sel, pdata=None, mode
         red, sol, aux = oc.gradIterBatch(ini_states, horizon, np.asarray(theta, dtype=float), taus, waypoints, sel,
                                          pdata=pdata, mode=mode)
         v = np.asarray(mem.to_host(red), dtype=float)
-        bad = np.asarray(mem.to_host(sol["status"])) != 1
-        if bad.any():
-            raise FloatingPointError("forward solve did not converge for %d OCP(s)" % int(bad.sum()))
+        n_failed = int(round(float(np.asarray(mem.to_host(aux["n_failed"]))[0])))
+        if n_failed:
+            st = np.asarray(mem.to_host(sol["status"]))
+            ast = np.asarray(mem.to_host(aux["aux_status"]))
+            raise FloatingPointError("CPDP gradient iteration failed for %d OCP(s): forward solve not converged for %d, "
+                                     "auxiliary sweep failed for %d (the reference would step on garbage or crash in "
+                                     "solve_ivp here)" % (n_failed, int((st != 1).sum()), int((ast != 0).sum())))
         return float(v[0]), v[1:].copy()
     return fn
+
+
+METHOD_IDS = {"Vanilla": 0, "Nesterov": 1, "Adam": 2, "Nadam": 3, "AMSGrad": 4}
+
+
+class DeviceLearner:
+    """The same learner with the whole loop on the GPU: evaluation point, CPDP gradient iteration, update, projection, stop
+    rule and traces are kernel launches on one stream (``cpdp_optim_step`` around ``COCSys.gradIterBatch``), nothing returns
+    to the host until ``run`` reads the traces at the end.  Same dictionary keys as ``Learner`` /
+    ``QuadAlgorithm.load_optimization_function`` (lib/QuadAlgorithm.py:132-191).  The per-iteration failure count of the
+    gradient iteration is accumulated on the device and checked once after the run.
+
+    Difference from the reference, stated: once the stop rule fires the remaining launches of the run are no-ops on the
+    parameter (the stream cannot `break`); ``check_every`` > 0 makes the host poll the stop flag every that many iterations
+    and leave early."""
+
+    def __init__(self, oc, ini_states, horizon, taus, waypoints, sel, pdata=None, mode=None, rounds=0, chunks=1):
+        self.oc = oc
+        self.args = (ini_states, horizon, taus, waypoints, sel)
+        self.kw = dict(pdata=pdata, mode=mode, rounds=rounds, chunks=chunks)
+        self.n_auxvar = oc.n_auxvar
+        self.loss_trace = []
+        self.parameter_trace = []
+
+    def load_optimization_function(self, para_input: dict):
+        m = para_input["method"]
+        if m not in METHOD_IDS:
+            raise Exception("Wrong optimization method type!")
+        self.method = METHOD_IDS[m]
+        self.learning_rate = float(para_input["learning_rate"])
+        self.iter_num = int(para_input["iter_num"])
+        self.mu = float(para_input.get("mu", 0.0))
+        self.true_loss = bool(para_input.get("true_loss_print_flag", False)) and m == "Nesterov"
+        self.beta_1 = float(para_input.get("beta_1", 0.0))
+        self.beta_2 = float(para_input.get("beta_2", 0.0))
+        self.epsilon = float(para_input.get("epsilon", 0.0))
+
+    def run(self, initial_parameter, check_every=0, loss_stop=0.9, grad_stop=0.05):
+        oc = self.oc
+        lib = oc.build()
+        mem = oc._device()
+        r, cap = self.n_auxvar, self.iter_num
+        th0 = np.array(initial_parameter, dtype=float).reshape(r)
+        theta = mem.from_host(th0)
+        theta_eval = mem.from_host(th0.reshape(1, r))
+        state = mem.zeros((3, r))
+        it = mem.zeros((2,), "i4")
+        loss_trace = mem.zeros((cap,))
+        ptrace = mem.zeros((cap + 1, r))
+        ptrace[0] = theta
+        failed = mem.zeros((1,))
+        x0, horizon, taus, wp, sel = self.args
+        # inputs go to the device once; every iteration then reads them (and theta_eval) in place
+        x0 = mem.from_host(np.asarray(x0, dtype=float).reshape(-1, oc.n_state)) if not hasattr(x0, "data_ptr") else x0
+        B = int(x0.shape[0])
+        taus = mem.from_host(np.asarray(taus, dtype=float).reshape(-1, np.asarray(taus).shape[-1])) if not hasattr(taus, "data_ptr") else taus
+        wp = mem.from_host(np.asarray(wp, dtype=float).reshape(B, -1, len(sel))) if not hasattr(wp, "data_ptr") else wp
+        if self.kw["pdata"] is not None and not hasattr(self.kw["pdata"], "data_ptr"):
+            self.kw["pdata"] = mem.from_host(np.asarray(self.kw["pdata"], dtype=float).reshape(B, oc.n_pvar))
+        hyper = (self.method, self.learning_rate, self.mu, self.beta_1, self.beta_2, self.epsilon, float(loss_stop), float(grad_stop))
+
+        def step(phase, red, defer):
+            lib.optim_step(phase, *hyper, mem.ptr(theta), mem.ptr(theta_eval), mem.ptr(state), mem.ptr(red), mem.ptr(it),
+                           mem.ptr(loss_trace), mem.ptr(ptrace), cap, defer, mem.stream())
+
+        def evaluate():
+            full, sol, aux = oc.gradIterBatch(x0, horizon, theta_eval.reshape(r), taus, wp, sel, **self.kw)
+            failed.__iadd__(aux["n_failed"])
+            return full
+
+        for j in range(cap):
+            step(0, None, 0)
+            red = evaluate()
+            step(1, red, 1 if self.true_loss else 0)
+            if self.true_loss:
+                step(0, None, 1)
+                step(2, evaluate(), 0)
+            if check_every and (j + 1) % check_every == 0 and int(mem.to_host(it)[1]):
+                break
+        done = int(mem.to_host(it)[0])
+        nf = float(np.asarray(mem.to_host(failed))[0])
+        if nf:
+            raise FloatingPointError("%d CPDP evaluation(s) of the run had failed OCPs" % int(round(nf)))
+        self.loss_trace = np.asarray(mem.to_host(loss_trace))[:done].tolist()
+        self.parameter_trace = np.asarray(mem.to_host(ptrace))[:done + 1].tolist()
+        self.stopped_early = bool(int(mem.to_host(it)[1]))
+        return np.asarray(mem.to_host(theta), dtype=float).copy()

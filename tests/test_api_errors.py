@@ -101,3 +101,44 @@ def test_ragged_waypoint_times(pend):
     a2 = pend.auxSysSolverBatch(sol, np.array([[0.0, 1.0], [0.0, 1.0]]), wp, [0])
     assert np.array_equal(a1["dtheta"], a2["dtheta"]) and np.array_equal(a1["loss"], a2["loss"])
     assert np.array_equal(a1["dtheta"][0], a1["dtheta"][1])
+
+
+def test_failures_travel_with_the_sum(pend):
+    """gradIterBatch reports the number of failed OCPs next to the reduced row (device-side, cpdp_pack_rows +
+    cpdp_reduce_rows); a fixed number of Newton rounds that is too small leaves problems `running` and must not pass as a
+    valid (all-zero) gradient; cpdp_grad_fn raises on it."""
+    from lfsd_b200.optim import cpdp_grad_fn
+    th = np.array([1.0, 0.5, 1.5])
+    x0 = np.zeros((3, 2))
+    wp = np.full((3, 1, 1), 1.0)
+    pend.aux_mode = pend.MODE_RK45
+    red, sol, aux = pend.gradIterBatch(x0, 1.0, th, np.array([0.5]), wp, [0])
+    assert float(aux["n_failed"][0]) == 0.0 and red.shape == (4,)
+    full = pend.reduceRows(pend.packRows(sol, aux))
+    assert np.array_equal(full[:4], red) and np.array_equal(red, pend.reduceBatch(aux["loss"], aux["dtheta"]))
+    red2, sol2, aux2 = pend.gradIterBatch(x0, 1.0, th, np.array([0.5]), wp, [0], rounds=2)     # needs 6-7 rounds
+    assert [int(v) for v in sol2["status"]] == [0, 0, 0]
+    assert float(aux2["n_failed"][0]) == 3.0 and np.all(red2 == 0.0)
+    # an out-of-range waypoint time is an error status, not an extrapolation (scipy's interp1d raises in the reference)
+    aux3 = pend.auxSysSolverBatch(sol, np.array([[0.5], [1.2], [-0.1]]), wp, [0])
+    assert [int(v) for v in aux3["aux_status"]] == [0, 5, 5]
+    assert float(aux3["loss"][1]) == 0.0 and np.all(aux3["dtheta"][1:] == 0.0)
+    assert float(pend.reduceRows(pend.packRows(sol, aux3))[4]) == 2.0
+    fn = cpdp_grad_fn(pend, x0, 1.0, np.array([1.5]), wp, [0], mode=pend.MODE_RK45)
+    with pytest.raises(FloatingPointError, match="failed for 3 OCP"):
+        fn(th)
+    # max_iter beyond the filter capacity is an argument error, not a silent clamp
+    args, keep = _solve_args(pend.build())
+    bad = list(args); bad[11] = 256
+    assert pend.build().L.cpdp_solve(*bad) == -10
+
+
+def test_reference_shaped_aux_rejects_what_it_cannot_integrate(pend):
+    th = np.array([1.0, 0.5, 1.5])
+    tg, opt_sol = pend.cocSolver([0.0, 0.0], 1, th, interplation_level=2)
+    with pytest.raises(NotImplementedError, match="linear"):
+        pend.auxSysSolver(tg, opt_sol, th)
+    tg, opt_sol = pend.cocSolver([0.0, 0.0], 1, th)
+    tg2 = tg.copy(); tg2[3] += 0.01
+    with pytest.raises(NotImplementedError, match="uniform"):
+        pend.auxSysSolver(tg2, opt_sol, th)

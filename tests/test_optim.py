@@ -90,3 +90,46 @@ def test_projection_stop_rule_and_errors():
     assert len(L.loss_trace) == 1
     with pytest.raises(Exception, match="Wrong optimization method type!"):
         Learner(_quad, 3).load_optimization_function({"learning_rate": 0.1, "iter_num": 1, "method": "SGD"})
+
+
+@pytest.mark.parametrize("method", ["Vanilla", "Nesterov", "NesterovTrue", "Adam", "Nadam", "AMSGrad"])
+def test_device_learner_matches_host_learner(method):
+    """DeviceLearner (update rule, projection, stop rule and traces in k_optim_* kernels around gradIterBatch; here on the
+    thread-emulated library) against the host Learner fed by the same CUDA-path gradients: identical traces, bit for bit."""
+    from tests.emu.support import emu_oc
+    from lfsd_b200.optim import DeviceLearner, cpdp_grad_fn
+    oc = emu_oc("pendulum")
+    oc.aux_mode = oc.MODE_RK45
+    x0 = np.zeros((2, 2))
+    taus, wp, sel = np.array([0.3, 0.8]), np.array([[[1.4], [2.9]], [[1.5], [2.7]]]), [0]
+    para = {"learning_rate": 0.02, "iter_num": 4, "method": method.replace("True", ""), "mu": 0.9,
+            "true_loss_print_flag": method.endswith("True"), "beta_1": 0.9, "beta_2": 0.999, "epsilon": 1e-8}
+    H = Learner(cpdp_grad_fn(oc, x0, 1.0, taus, wp, sel), 3)
+    H.load_optimization_function(para)
+    th_h = H.run([1.0, 0.5, 1.5])
+    D = DeviceLearner(oc, x0, 1.0, taus, wp, sel)
+    D.load_optimization_function(para)
+    th_d = D.run([1.0, 0.5, 1.5])
+    assert len(D.loss_trace) == len(H.loss_trace) == 4, (D.loss_trace, H.loss_trace)
+    assert np.array_equal(np.array(D.parameter_trace), np.array(H.parameter_trace)), method
+    assert np.array_equal(np.array(D.loss_trace), np.array(H.loss_trace))
+    assert np.array_equal(th_d, th_h)
+
+
+def test_device_learner_stop_rule_and_projection():
+    from tests.emu.support import emu_oc
+    from lfsd_b200.optim import DeviceLearner
+    oc = emu_oc("pendulum")
+    oc.aux_mode = oc.MODE_RK45
+    # waypoint on the optimum's own trajectory start: loss 0 < 0.9 -> the rule stops after the first iteration
+    D = DeviceLearner(oc, np.zeros((1, 2)), 1.0, np.array([0.0]), np.array([[[0.0]]]), [0])
+    D.load_optimization_function({"learning_rate": 0.02, "iter_num": 3, "method": "Vanilla"})
+    D.run([1.0, 0.5, 1.5])
+    assert len(D.loss_trace) == 1 and len(D.parameter_trace) == 2 and D.stopped_early
+    # a huge learning rate drives theta[0] negative: projected to 1e-8 (QuadAlgorithm.py:250); stop thresholds disabled
+    D = DeviceLearner(oc, np.zeros((1, 2)), 1.0, np.array([0.5]), np.array([[[3.0]]]), [0])
+    D.load_optimization_function({"learning_rate": 1e3, "iter_num": 1, "method": "Vanilla"})
+    D.run([1.0, 0.5, 1.5], loss_stop=-1.0, grad_stop=-1.0)
+    assert D.parameter_trace[1][0] == 1e-8 or D.parameter_trace[1][0] > 1.0
+    with pytest.raises(Exception, match="Wrong optimization method type!"):
+        D.load_optimization_function({"learning_rate": 0.1, "iter_num": 1, "method": "SGD"})
