@@ -84,11 +84,14 @@ def _sparse_tables(name, M):
             if M[i, j] != 0:
                 rowidx.append(i)
         colptr.append(len(rowidx))
+    coor = [i for i in range(nr) for j in range(nc) if M[i, j] != 0]      # COO list in row-major order: folds to constants
+    cooc = [j for i in range(nr) for j in range(nc) if M[i, j] != 0]      # in fully unrolled loops (straight-line products)
     def arr(nm, v):
         v = v if v else [0]
-        return ("    CPDP_HD static int %s_%s(int i) { const int t[%d] = {%s}; return t[i]; }"
+        return ("    CPDP_HD static constexpr int %s_%s(int i) { constexpr int t[%d] = {%s}; return t[i]; }"
                 % (name, nm, len(v), ", ".join(map(str, v))))
     return "\n".join([arr("rowptr", rowptr), arr("colidx", colidx), arr("colptr", colptr), arr("rowidx", rowidx),
+                      arr("coor", coor), arr("cooc", cooc),
                       "    static constexpr int %s_nnz = %d;" % (name, len(colidx))])
 
 
@@ -169,6 +172,9 @@ def generate_model_header(name, state, control, auxvar, dyn, path_cost, final_co
                     assigns.append(("M[%d]" % (off + i * M.shape[1] + j), M[i, j]))
         off += M.shape[0] * M.shape[1]
     offs.append("    static constexpr int PMP_SIZE = %d;" % off)
+    huu = mats[6][1]
+    offs.append("    static constexpr bool HUU_DIAG = %s;      // structurally diagonal Huu: its inverse is NU reciprocals"
+                % ("true" if all(huu[i, j] == 0 for i in range(m) for j in range(m) if i != j) else "false"))
     body, info["ops_pmp"] = _emit_body(assigns)
     body = body.replace("mu[", "lam[")
     parts.append("    CPDP_HD static void pmp(const double* __restrict__ x, const double* __restrict__ u, "

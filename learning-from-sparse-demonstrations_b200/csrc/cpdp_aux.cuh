@@ -165,6 +165,16 @@ CPDP_D double xul_at(const AuxProblem& p, double t, int e) {
 // PMP matrices + inv(Huu) of one slot from its interpolated (x, u, lam); executed by ONE thread
 CPDP_D bool pmp_eval(const AuxProblem& p, const double* xul, double* M) {
     Model::pmp(xul, xul + NX, xul + NX + NU, p.th, p.pd, M);
+    if (Model::HUU_DIAG) {           // every JinEnv model: Huu = diag (control-effort weights); the general inverse stays for user models
+        bool ok = true;
+        double* Hi = M + Model::PMP_SIZE;
+        for (int i = 0; i < NU; ++i) {
+            const double d = M[Model::PMP_HUU + i * NU + i];
+            if (!(fabs(d) > 0.0)) ok = false;
+            for (int j = 0; j < NU; ++j) Hi[i * NU + j] = (i == j) ? 1.0 / d : 0.0;
+        }
+        return ok;
+    }
     return inv_small<NU>(M + Model::PMP_HUU, M + Model::PMP_SIZE);
 }
 

@@ -48,42 +48,3 @@ static void emu_launch(F kernel, int grid, int block, size_t smem, Args... args)
 #define CPDP_PREPARE_SMEM(kernel, bytes) (void)0
 #define CPDP_LAST_ERROR() 0
 #include "cpdp_api.inl"
-
-// ---- unit-test hook (emulation only): Schur form, "LU" event and one Newton solve of the BDF kernel on a given L, C
-#ifdef CPDP_WITH_BDF
-namespace CPDP_NS {
-void k_emu_bdf_linear(const double* L, const double* Cm, double c, const double* rhs, double* out_TZ, double* out_sol, int* ok) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    BDF_LAYOUT();
-    {
-        int* s_ti = (int*)s.ti; int* s_tj = (int*)s.tj;
-        for (int q = tid; q < NT; q += nt) {
-            int i = 0, rem = q;
-            while (rem >= NX - i) { rem -= NX - i; ++i; }
-            s_ti[q] = i; s_tj[q] = i + rem;
-        }
-    }
-    for (int i = tid; i < NX * NX; i += nt) bs.Lm[i] = L[i];
-    for (int i = tid; i < NX * NP; i += nt) bs.Cm[i] = Cm[i];
-    for (int i = tid; i < NYR; i += nt) bs.dy[i] = rhs[i];
-    __syncthreads();
-    bool good = bdf_schur();
-    if (good) good = bdf_factor(c);
-    if (good) bdf_solve(c);
-    __syncthreads();
-    for (int i = tid; i < NX * NX; i += nt) {
-        out_TZ[i] = bs.Tr[i]; out_TZ[NX * NX + i] = bs.Ti[i]; out_TZ[2 * NX * NX + i] = bs.Zr[i]; out_TZ[3 * NX * NX + i] = (i < 4 * NX) ? bs.ga[i] : 0.0;   // ga | gbr | gbi | pi (contiguous)
-        out_TZ[4 * NX * NX + i] = bs.Winv[i];
-    }
-    for (int i = tid; i < NYR; i += nt) out_sol[i] = bs.dy[i];
-    if (tid == 0) *ok = good ? 1 : 0;
-}
-}  // namespace CPDP_NS
-
-extern "C" CPDP_API int cpdp_emu_bdf_linear(const double* L, const double* Cm, double c, const double* rhs, double* out_TZ, double* out_sol) {
-    int ok = 0;
-    emu_launch(CPDP_NS::k_emu_bdf_linear, 1, CPDP_NS::BDF_THREADS, CPDP_NS::BDF_SMEM_BYTES,
-               L, Cm, c, rhs, out_TZ, out_sol, &ok);
-    return ok;
-}
-#endif

@@ -373,3 +373,67 @@ def test_chunked_streams_bit_identical(torch_mod):
             assert torch.equal(sol1[k], sol2[k]), k
         for k in ("Xa", "Ua", "loss", "dtheta", "counters"):
             assert torch.equal(aux1[k], aux2[k]), k
+
+
+def test_stored_run_all_100_triples(torch_mod):
+    """Every (theta, loss, dL/dtheta) triple the reference's stored run pins, in ONE batched call (B = 100, one parameter
+    vector per problem, non-accumulating): iteration j of the stored Nesterov run evaluated loss_trace[j] and the gradient
+    g_j = (mu v_j - v_{j+1}) / lr at the look-ahead point theta_j + mu v_j (lib/QuadAlgorithm.py:480-486).
+    Tolerances: loss 1e-8, dL/dtheta 1e-5 relative (north_star), both against the reference's numbers; and against the oracle
+    (scipy BDF with the closed-form Jacobian) where the fixture exists."""
+    from tests.golden.make_stored_run_triples import triples
+    g = np.load(os.path.join(HERE, "golden", "quad_run.npz"))
+    look, losses, grads = triples(g)
+    assert look.shape == (100, 7)
+    oc = _oc("quadrotor", 25)
+    if not _has_bdf(oc):
+        pytest.skip("library built without the BDF sweep")
+    oc.aux_mode = oc.MODE_BDF
+    oc.rtol_back, oc.atol_back, oc.rtol_fwd, oc.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
+    B = 100
+    sol = oc.cocSolverBatch(np.tile(g["ini_state"], (B, 1)), 1.0, look, pdata=np.tile(g["goal_position"].reshape(1, 3), (B, 1)))
+    assert (_np(sol["status"]) == 1).all()
+    aux = oc.auxSysSolverBatch(sol, g["time_grid"], np.tile(g["waypoints"], (B, 1, 1)), [0, 1, 2])
+    assert (_np(aux["aux_status"]) == 0).all()
+    loss, dth = _np(aux["loss"]), _np(aux["dtheta"])
+    lerr = np.abs(loss - losses) / losses
+    gerr = np.linalg.norm(dth - grads, axis=1) / np.linalg.norm(grads, axis=1)
+    print("stored run, 100 triples: max loss err %.2e, max dL/dtheta err %.2e (at j=%d)" % (lerr.max(), gerr.max(), int(gerr.argmax())))
+    assert lerr.max() < 1e-8, (int(lerr.argmax()), lerr.max())
+    assert gerr.max() < GRAD_RTOL, (int(gerr.argmax()), gerr.max())
+    p = os.path.join(HERE, "golden", "stored_run_triples.npz")
+    if os.path.exists(p):
+        fx = np.load(p)
+        assert np.array_equal(_np(sol["iters"]), fx["iters"])
+        oerr = np.linalg.norm(dth - fx["dl_cj"], axis=1) / np.linalg.norm(fx["dl_cj"], axis=1)
+        assert oerr.max() < GRAD_RTOL, (int(oerr.argmax()), oerr.max())
+
+
+def test_bdf_counters_equal_scipy(torch_mod):
+    """k_riccati_bdf takes exactly scipy's decisions: right-hand-side evaluations, accepted steps, LU factorisations and
+    Jacobian evaluations of every fixture problem equal those of scipy's BDF class (closed-form Jacobian) stepped over the same
+    intervals (tests/golden/make_counter_fixture.py); forward RK45 right-hand-side counts equal solve_ivp's."""
+    p = os.path.join(HERE, "golden", "oracle_counters.npz")
+    if not os.path.exists(p):
+        pytest.skip("counter fixture missing")
+    cf = np.load(p)
+    for case, model, sel in (("pendulum", "pendulum", [0]), ("robotarm", "robotarm", [0, 1]), ("rocket", "rocket", [0, 1, 2, 6, 7, 8, 9]),
+                             ("quadkat", "quadrotor", [0, 1, 2]), ("quad50", "quadrotor", [0, 1, 2])):
+        fx = _fx(case)
+        oc = _oc(model, int(fx["n_grid"]))
+        if not _has_bdf(oc):
+            pytest.skip("library built without the BDF sweep")
+        oc.aux_mode = oc.MODE_BDF
+        oc.rtol_back, oc.atol_back, oc.rtol_fwd, oc.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
+        pd = fx["pdata"] if "pdata" in fx.files else None
+        sol = oc.cocSolverBatch(fx["x0"], float(fx["T"]), fx["theta"], pdata=pd)
+        aux = oc.auxSysSolverBatch(sol, fx["taus"], fx["wp"], sel)
+        cnt = _np(aux["counters"])
+        conv = fx["kkt"] < 1e-10
+        want = cf[case]                                   # [nfev, steps, nlu, njev] per problem, -1 where scipy gave up
+        for b in np.flatnonzero(conv):
+            if want[b][0] < 0 or int(_np(aux["aux_status"])[b]) != 0:
+                continue
+            got = [int(cnt[b][0]), int(cnt[b][1]), int(cnt[b][4]), int(cnt[b][5])]
+            assert got == [int(v) for v in want[b]], (case, b, got, want[b].tolist())
+            assert int(cnt[b][2]) == int(fx["cnt_asshipped_cj"][b][1]), (case, b)      # forward RK45 rhs evaluations

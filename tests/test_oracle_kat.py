@@ -69,3 +69,24 @@ def test_k5_second_gradient(run, orc):
     loss, dl, _ = orc.grad_iter(run["ini_state"], 1.0, look, run["time_grid"], run["waypoints"])
     assert abs(loss - run["loss_trace"][1]) / run["loss_trace"][1] < 1e-9
     assert np.linalg.norm(dl - g1) / np.linalg.norm(g1) < 1e-6
+
+
+def test_all_100_stored_triples_fixture(run):
+    """The oracle at every one of the 100 (theta, loss, dL/dtheta) triples of the stored run (generated once by
+    tests/golden/make_stored_run_triples.py, ~20 CPU-minutes; K3-K5 above recompute two of them live).
+    cj = scipy BDF handed the closed-form Jacobian: within 1e-6 of the reference's gradient at ALL 100 points.
+    fd = scipy 1.18.1's BDF with its finite-difference Jacobian (the as-shipped call): leaves 1e-5 at a few late points --
+    the reference's stored numbers come from another scipy / BLAS build, and the finite-difference Jacobian amplifies
+    roundoff to that level, which is why the CUDA kernel is held to cj."""
+    from tests.golden.make_stored_run_triples import triples
+    p = os.path.join(HERE, "golden", "stored_run_triples.npz")
+    if not os.path.exists(p):
+        pytest.skip("fixture not generated")
+    fx = np.load(p)
+    look, losses, grads = triples(run)
+    assert np.array_equal(fx["theta"], look) and np.array_equal(fx["grad_ref"], grads)
+    rel = lambda a, b: np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+    assert np.abs(fx["loss_cj"] - losses).max() / losses.min() < 1e-8
+    assert rel(fx["dl_cj"], grads).max() < 1e-6
+    bad_fd = np.flatnonzero(rel(fx["dl_fd"], grads) > 1e-5)
+    assert len(bad_fd) <= 5 and (len(bad_fd) == 0 or bad_fd.min() >= 20), bad_fd        # documented: a few late points

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Developer tool (not part of the product path): builds tuning variants of the quadrotor library (CTA size of
+"""Developer tool (not part of the product path): builds tuning variants of the quadrotor library (residency of
 k_riccati_bdf, optional clock64 phase instrumentation) and times the backward sweep alone at several batch sizes.
 
   python tools/prof_bdf_phases.py --build-only            (here: cross-compiles the variants into lib/)
@@ -16,10 +16,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
-    "t32": [],
-    "t32time": ["-DCPDP_BDF_TIMING"],
-    "t64": ["-DCPDP_BDF_THREADS=64", "-DCPDP_BDF_MINB=4"],
-    "t128": ["-DCPDP_BDF_THREADS=128", "-DCPDP_BDF_MINB=2"],
+    "base": [],
+    "time": ["-DCPDP_BDF_TIMING"],
+    "minb6": ["-DCPDP_BDF_MINB=6"],
+    "minb10": ["-DCPDP_BDF_MINB=10"],
 }
 PHASES = ["prepare", "rhs", "jacobian", "schur", "factor", "solve", "norm", "change_D", "total"]
 
