@@ -37,7 +37,7 @@ namespace CPDP_NS {
 constexpr int BDF_THREADS = 32;
 constexpr int NC = NX + NP;                      // columns of S = [P | W]: one lane each
 static_assert(NC <= 32, "k_riccati_bdf maps one lane per column of [P | W]");
-static_assert(NX <= 16, "warp sections of the Schur iteration map one lane per row/column and 16 + lane per row of Z");
+static_assert(NX <= 16 && NP <= 16, "warp sections map one lane per row/column and 16 + lane for the second half / the rows of Z");
 #ifndef CPDP_BDF_MINB
 #define CPDP_BDF_MINB 8
 #endif
@@ -46,12 +46,24 @@ constexpr int BDF_NEWTON_MAXITER = 4;
 constexpr int BDF_NROWS = BDF_MAX_ORDER + 3;
 constexpr int BDF_WS_DOUBLES = BDF_NROWS * NX * NC;      // differences array of one problem, [row][i][c]
 
+// code-size / instruction-level-parallelism knobs of the hot loop.  Measured (tools/prof_bdf_phases.py, 4096 OCPs / one OCP per SM):
+// fully unrolled product + stencils x4: 183 ms / 20.0 ms; rolled: 141 ms / 21.1 ms -- eight warps per SM at different phases of
+// the integrator share a 32 KB instruction cache, so code size beats instruction-level parallelism.
+#ifndef CPDP_BDF_LMUL_UNROLL
+#define CPDP_BDF_LMUL_UNROLL 1
+#endif
+#ifndef CPDP_BDF_STENCIL_UNROLL
+#define CPDP_BDF_STENCIL_UNROLL 1
+#endif
 #ifdef __CUDACC__
 #define BDF_SYNC() __syncwarp()
 #define BDF_UNROLL _Pragma("unroll")
+#define BDF_PRAGMA_STR(x) _Pragma(#x)
+#define BDF_PRAGMA_UNROLL(n) BDF_PRAGMA_STR(unroll n)
 #else
 #define BDF_SYNC() __syncthreads()
 #define BDF_UNROLL
+#define BDF_PRAGMA_UNROLL(n)
 #endif
 
 CPDP_HD double bdf_kappa(int k) { const double v[6] = {0.0, -0.1850, -1.0 / 9, -0.0823, -0.0415, 0.0}; return v[k]; }
@@ -68,8 +80,11 @@ CPDP_D double bdf_mul(double a, double b) { volatile double r = a * b; return r;
 #endif
 
 // Shared-memory layout of one problem: compile-time offsets (in doubles) into the dynamic block.
-constexpr int QS = (NX + 1) & ~1;                // row stride of the k-major product operands (even: 128-bit loads)
+constexpr int QS = (NX + 1) & ~1;                // row stride of the k-major product operands
 constexpr int NCS = NC | 1;                      // odd row stride of the column exchange buffers (conflict-free transposes)
+constexpr int SWQ = (NX - 1 + 3) / 4;            // Lyapunov sweep: terms per lane and sum (4 lanes per entry)
+constexpr int TW = 4 * SWQ;                      // row width of the skewed T: T2S[r][t] = T[r][r + 1 + t], zero beyond the matrix
+constexpr int NH = (NX + 1) / 2;                 // rows per half in the two-halves products (lanes c and 16 + c)
 namespace bo {
 constexpr int M = 0;                             // PMP matrices at the current time + inverse of Huu
 constexpr int XUL = M + ((MSZ + 1) & ~1);        // interpolated (x, u, lambda)
@@ -77,27 +92,35 @@ constexpr int RED = XUL + ((2 * NX + NU + 1) & ~1);   // reduction scratch (host
 constexpr int Q = RED + 66;                      // real Schur vectors Q[k][i], row stride QS: k-major operand of Q' x
 constexpr int QT = Q + NX * QS;                  // Q'[k][i] = Q[i][k]: k-major operand of Q x
 constexpr int WT = QT + NX * QS;                 // ((I + c L)^{-1})'[k][i]: k-major operand of (I + cL)^{-1} x
-constexpr int TR = WT + NX * QS;                 // T = Z^H L Z, upper triangular complex (Z = Q G^H), row stride NX
-constexpr int TI = TR + NX * NX;
-constexpr int YR = TI + NX * NX;                 // Lyapunov sweep: right-hand side in, Hermitian solution out
-constexpr int YI = YR + NX * NX;
-constexpr int DR = YI + NX * NX;                 // 1 / ((1/2 + c t_ii) + conj(1/2 + c t_jj)), [i][j], i <= j
-constexpr int DI = DR + NX * NX;
-constexpr int CM = DI + NX * NX;                 // C = R W - r_ at the Jacobian point, [NX][NP]
-constexpr int XA = CM + NX * NP;                 // column exchange buffers, [NX][NCS]
+constexpr int LM = WT + NX * QS;                 // L = A' - P R at the Jacobian point, row-major (kept for the "LU" events)
+constexpr int Y2 = LM + ((NX * NX + 1) & ~1);    // Lyapunov sweep: right-hand side in, Hermitian solution out; complex, [k][j]
+constexpr int T2S = Y2 + 2 * NX * NX;            // T = Z^H L Z above the diagonal, complex, skewed rows of width TW.  MUST follow
+                                                 // Y2: the sweep's zero-weighted reads past Y2 land here (finite values)
+constexpr int TD = T2S + 2 * NX * TW;            // diagonal of T, complex
+constexpr int PV = TD + 2 * NX;                  // Lyapunov pivots 1 / (1 + c (t_ii + conj t_jj)), complex, [i][j], i <= j;
+                                                 // during the Schur iteration: the plain n x n work arrays Tr | Ti
+constexpr int CM = PV + 2 * NX * NX;             // C = R W - r_ at the Jacobian point, [NX][NP]
+constexpr int XA = CM + ((NX * NP + 1) & ~1);    // column exchange buffers, [NX][NCS]
 constexpr int XB = XA + NX * NCS;
 constexpr int GHM = XB + NX * NCS;               // fu Huu^{-1}, [NX][NU]
-constexpr int YM = GHM + NX * NU;                // Y = fu'P + Hux, [NU][NX]   (Jacobian scratch)
-constexpr int YPM = YM + NU * NX;                // Huu^{-1} Y, [NU][NX]
+constexpr int YPM = GHM + NX * NU;               // Huu^{-1} Y, [NU][NX]
 constexpr int ROT = YPM + NU * NX;               // block rotations G: ga | gbr | gbi | partner   (4 x NX)
-constexpr int SD = ROT + 4 * NX;                 // 1 / (1 + c t_ii): re | im   (also Householder vector scratch)
-constexpr int RU = SD + 2 * NX;                  // change_D: RU | R | U, 6 x 6 each
+constexpr int RU = ROT + 4 * NX;                 // change_D: RU | R | U, 6 x 6 each (also Householder vector scratch)
 constexpr int FLAG = RU + 108;                   // 2 ints
 constexpr int END = FLAG + 2;
-static_assert(Q % 2 == 0 && QT % 2 == 0 && WT % 2 == 0, "128-bit shared-memory loads need 16-byte aligned operands");
+static_assert(Y2 % 2 == 0 && T2S % 2 == 0 && TD % 2 == 0 && PV % 2 == 0, "complex arrays are read with 128-bit loads");
 }  // namespace bo
 constexpr int BDF_SMEM_DOUBLES = bo::END;
 constexpr size_t BDF_SMEM_BYTES = (size_t)BDF_SMEM_DOUBLES * sizeof(double);
+
+struct cplx { double x, y; };                    // (host emulation has no double2)
+#ifdef __CUDACC__
+#define BDF_LD2(p) (*reinterpret_cast<const double2*>(p))
+#define BDF_ST2(p, a, b) (*reinterpret_cast<double2*>(p) = make_double2((a), (b)))
+#else
+#define BDF_LD2(p) (*reinterpret_cast<const cplx*>(p))
+#define BDF_ST2(p, a, b) do { (p)[0] = (a); (p)[1] = (b); } while (0)
+#endif
 
 #define BDF_SM() CPDP_DYN_SMEM(sm)
 
@@ -129,28 +152,41 @@ CPDP_D double bdf_rcp(double x) {
 #endif
 }
 
-// out[i] = sum_k AT[k][i] x[k*xs]: the contraction index is ROLLED (the instruction caches hold 6 KB / 32 KB: a fully
-// unrolled 13 x 13 product is 340 instructions and the hot loop needs ten of them), the NX accumulators are independent
-// register chains fed by broadcast 128-bit loads of a k-major operand; x comes from shared memory (a column of an exchange
-// buffer, stride NCS, or a row, stride 1).  Summation order: ascending k.
-CPDP_D void bdf_lmul_k(const double* __restrict__ AT, const double* __restrict__ x, const int xs, double (&out)[NX]) {
-    BDF_UNROLL for (int i = 0; i < NX; ++i) out[i] = 0.0;
-#ifdef __CUDACC__
-#pragma unroll 2
-#endif
-    for (int k = 0; k < NX; ++k) {
-        const double xk = x[k * xs];
-#ifdef __CUDACC__
-        const double2* row = reinterpret_cast<const double2*>(AT + k * QS);
-        BDF_UNROLL for (int i2 = 0; i2 < NX / 2; ++i2) {
-            const double2 a = row[i2];
-            out[2 * i2] += a.x * xk; out[2 * i2 + 1] += a.y * xk;
-        }
-        if (NX & 1) out[NX - 1] += AT[k * QS + NX - 1] * xk;
+// Developer instrumentation (-DCPDP_BDF_TIMING): per-phase clock64() totals of each problem, written over the Ua rows of
+// the problem at kernel end (phases = 1 runs only; tools/prof_bdf_phases.py).  Off in the shipped library.
+#ifdef CPDP_BDF_TIMING
+#define BDF_T(ph, ...) do { const long long t0__ = clock64(); __VA_ARGS__; tp[ph] += clock64() - t0__; } while (0)
+#define BDF_TB(ph, var, expr) do { const long long t0__ = clock64(); var = (expr); tp[ph] += clock64() - t0__; } while (0)
+#define BDF_TP_PARAM , long long* tp
+#define BDF_TP_ARG , tp
 #else
-        for (int i = 0; i < NX; ++i) out[i] += AT[k * QS + i] * xk;
+#define BDF_T(ph, ...) do { __VA_ARGS__; } while (0)
+#define BDF_TB(ph, var, expr) do { var = (expr); } while (0)
+#define BDF_TP_PARAM
+#define BDF_TP_ARG
 #endif
+
+// THE product of the hot loop, one out-of-line instance:  dst[(i0 + i) * ds] = sum_k AT[k][i0 + i] x[k * xs],  i < NH.
+// All operands in shared memory; AT is k-major with row stride `as` (broadcast loads), x a column (stride NCS) or a row
+// (stride 1) of an exchange buffer.  Two lanes share one output column (rows [0, NH) and [NX - NH, NX)), so a 13 x 13 product
+// occupies 26 lanes with 7 independent accumulator chains each; k is fully unrolled (every load in flight at once) --
+// affordable because this is the only copy.  Summation order: ascending k.
+CPDP_D_NOINLINE void bdf_lmul_to(const double* __restrict__ AT, const int as, const double* __restrict__ x, const int xs,
+                                 double* __restrict__ dst, const int ds, const int i0) {
+    double out[NH];
+    BDF_UNROLL for (int i = 0; i < NH; ++i) out[i] = 0.0;
+    const double* A0 = AT + i0;
+    BDF_PRAGMA_UNROLL(CPDP_BDF_LMUL_UNROLL) for (int k = 0; k < NX; ++k) {
+        const double xk = x[k * xs];
+        BDF_UNROLL for (int i = 0; i < NH; ++i) out[i] += A0[k * as + i] * xk;
     }
+    BDF_UNROLL for (int i = 0; i < NH; ++i) dst[(i0 + i) * ds] = out[i];
+}
+// lane -> (column, first row) of the two-halves mapping; false for idle lanes
+CPDP_D bool bdf_half(const int lane, int& col, int& i0) {
+    col = lane & 15;
+    i0 = (lane >> 4) ? NX - NH : 0;
+    return col < NX;
 }
 // column exchange helpers: buf is [NX][NCS]
 CPDP_D void bdf_put(double* buf, int c, const double (&v)[NX]) {
@@ -180,8 +216,7 @@ CPDP_D_NOINLINE bool bdf_prepare(const AuxProblem p, const double t) {
 //   YZ = fu'[P|W] + [Hux|Hue],  Yp = Huu^{-1} Y
 //   Pdot = -(Hxx + fx'P + (fx'P)' - sym(Y' Huu^{-1} Y))          Wdot = -fx'W - P fe - Hxe + Yp' Z
 // ------------------------------------------------------------------------------------------------
-template <bool SYM>
-CPDP_D void bdf_rhs_cols(double* sm, const double (&y)[NX], double (&f)[NX]) {
+CPDP_D void bdf_rhs_cols(double* sm, const double (&y)[NX], double (&f)[NX], const bool SYM) {
     const int c = threadIdx.x;
     const bool isP = c < NX, isW = (c >= NX) && (c < NC);
     const int k = isW ? c - NX : 0, cp = isP ? c : 0;
@@ -222,16 +257,16 @@ CPDP_D void bdf_rhs_cols(double* sm, const double (&y)[NX], double (&f)[NX]) {
         f[i] = -(((g[i] + gb[i * gs]) + hb[i * hs]) - yy);
     }
     BDF_SYNC();
-    if (SYM) {                                                           // bitwise symmetric P block (start-up of an interval:
-        if (isP) bdf_put(sm + bo::XB, c, f);                             // the value seeds the differences array)
+    if (SYM) {                                                           // bitwise symmetric P block
+        if (isP) bdf_put(sm + bo::XA, c, f);
         BDF_SYNC();
-        if (isP) { BDF_UNROLL for (int i = 0; i < NX; ++i) f[i] = 0.5 * (f[i] + sm[bo::XB + c * NCS + i]); }
+        if (isP) { BDF_UNROLL for (int i = 0; i < NX; ++i) f[i] = 0.5 * (f[i] + sm[bo::XA + c * NCS + i]); }
         BDF_SYNC();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Closed-form Jacobian data at (PMP matrices in shared memory, state columns y):  L = A' - P R -> TR (row-major),
+// Closed-form Jacobian data at (PMP matrices in shared memory, state columns y):  L = A' - P R -> LM (row-major),
 // C = R W - r_ -> CM, with A = fx - G Hxu', R = G fu', r_ = fe - G Hue, G = fu Huu^{-1}   (CPDP.py:262-270)
 // ------------------------------------------------------------------------------------------------
 CPDP_D_NOINLINE void bdf_jacobian() {
@@ -266,8 +301,7 @@ CPDP_D_NOINLINE void bdf_jacobian() {
             BDF_UNROLL for (int a = 0; a < NU; ++a) a1 -= G[j * NU + a] * Hxu[c * NU + a];
             double pr = 0.0;
             BDF_UNROLL for (int a = 0; a < NU; ++a) pr += pg[a] * fu[j * NU + a];
-            sm[bo::TR + c * NX + j] = a1 - pr;
-            sm[bo::TI + c * NX + j] = 0.0;
+            sm[bo::LM + c * NX + j] = a1 - pr;
         }
     } else if (isW) {
         double z[NU];                                                    // column k of Z = fu'W + Hue
@@ -319,6 +353,30 @@ CPDP_D double bdf_bcast(double* sm, double v, int src) {
     const double r = w[src];
     __syncthreads();
     return r;
+#endif
+}
+// lane holding the largest key among the lanes with pred (ties: the highest lane); key = 0 everywhere -> -1
+CPDP_D int bdf_argmax(double* sm, double v, bool pred) {
+#ifdef __CUDACC__
+    (void)sm;
+    const unsigned key = pred ? (unsigned)__double2hiint(fabs(v)) : 0u;      // high word: monotonic for non-negative doubles
+    const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+    if (mx == 0u) return -1;
+    return 31 - __clz((int)__ballot_sync(0xffffffffu, key == mx));
+#else
+    double* w = sm + bo::RED;
+    __syncthreads();
+    w[threadIdx.x] = pred ? fabs(v) : -1.0;
+    __syncthreads();
+    int best = -1; unsigned bk = 0;
+    for (int i = 0; i < 32; ++i) {
+        if (w[i] < 0.0) continue;
+        unsigned long long bits; memcpy(&bits, &w[i], 8);
+        const unsigned key = (unsigned)(bits >> 32);
+        if (key != 0u && key >= bk) { bk = key; best = i; }
+    }
+    __syncthreads();
+    return best;
 #endif
 }
 CPDP_D int bdf_top_bit(unsigned m) {            // index of the highest set bit (m != 0)
@@ -493,13 +551,15 @@ CPDP_D_NOINLINE bool bdf_schur() {
     BDF_SM();
     constexpr int n = NX;
     const int lane = threadIdx.x;
-    double* Tr = sm + bo::TR; double* Ti = sm + bo::TI; double* Zm = sm + bo::YR;        // Schur vectors, row stride n (scratch)
+    double* Tr = sm + bo::PV; double* Ti = Tr + n * n;                 // plain work arrays (the pivots are rebuilt by bdf_factor)
+    double* Zm = sm + bo::Y2;                                          // Schur vectors, row stride n (scratch)
     double* ga = sm + bo::ROT; double* gbr = ga + n; double* gbi = gbr + n; double* pi = gbi + n;
     int* flag = (int*)(sm + bo::FLAG);
     BDF_SYNC();
+    CPDP_LOOP for (int e = lane; e < n * n; e += BDF_THREADS) { Tr[e] = sm[bo::LM + e]; Ti[e] = 0.0; }
     if (lane == 0) flag[1] = 1;
     BDF_SYNC();
-    const bool ok = schur_real_w0(sm, Tr, Zm, sm + bo::SD);
+    const bool ok = schur_real_w0(sm, Tr, Zm, sm + bo::RU);
     BDF_SYNC();
     if (!ok && lane == 0) flag[1] = 0;
     // ---- one unitary rotation per 2 x 2 block:  G = [[c, s], [-conj(s), c]],  T <- G T G^H.  The Schur vectors stay REAL;
@@ -546,19 +606,24 @@ CPDP_D_NOINLINE bool bdf_schur() {
         BDF_SYNC();
     }
     BDF_SYNC();
-    // k-major product operands: Q[k][i] (for Q' x) and QT[k][i] = Q[i][k] (for Q x), row stride QS
+    // k-major product operands Q[k][i] (for Q' x) and QT[k][i] = Q[i][k] (for Q x); T packed for the sweep
     CPDP_LOOP for (int e = lane; e < n * n; e += BDF_THREADS) {
         const int r_ = e / n, c_ = e % n;
         const double v = Zm[e];
         sm[bo::Q + r_ * QS + c_] = v;
         sm[bo::QT + c_ * QS + r_] = v;
     }
+    CPDP_LOOP for (int e = lane; e < n * TW; e += BDF_THREADS) {
+        const int r_ = e / TW, k = r_ + 1 + e % TW;
+        BDF_ST2(sm + bo::T2S + 2 * e, k < n ? Tr[r_ * n + k] : 0.0, k < n ? Ti[r_ * n + k] : 0.0);
+    }
+    if (lane < n) BDF_ST2(sm + bo::TD + 2 * lane, Tr[lane * n + lane], Ti[lane * n + lane]);
     BDF_SYNC();
     return flag[1] != 0;
 }
 
-// 2 x 2 stencils of the block rotations on a matrix held in shared memory (row stride st):
-//   (G E G^H)[i][j]  for real symmetric E  ->  complex
+// 2 x 2 stencils of the block rotations on a matrix held in shared memory:
+//   (G E G^H)[i][j]  for real symmetric E (row stride st)  ->  complex
 CPDP_D void bdf_stencil_GEGh(const double* rot, const double* E, const int st, const int i, const int j, double& cr, double& ci) {
     constexpr int n = NX;
     const int pi = (int)rot[3 * n + i], pj = (int)rot[3 * n + j];
@@ -570,116 +635,103 @@ CPDP_D void bdf_stencil_GEGh(const double* rot, const double* E, const int st, c
     cr = ujr * gj_a + (upr * gj_br - upi * gj_bi);
     ci = uji * gj_a + (upr * gj_bi + upi * gj_br);
 }
-//   Re (G^H Y G)[i][j]  for complex Y (Yr, Yi, row stride n)
-CPDP_D double bdf_stencil_GhYG(const double* rot, const double* Yr, const double* Yi, const int i, const int j) {
+//   Re (G^H Y G)[i][j]  for the complex Y of the sweep
+CPDP_D double bdf_stencil_GhYG(const double* rot, const double* Y, const int i, const int j) {
     constexpr int n = NX;
     const int pi = (int)rot[3 * n + i], pj = (int)rot[3 * n + j];
     const double ai_r = rot[i], ap_r = rot[n + pi], ap_i = -rot[2 * n + pi];           // conj(G[i][i]), conj(G[pi][i])
     const double bj_r = rot[j], bp_r = rot[n + pj], bp_i = rot[2 * n + pj];            // G[j][j], G[pj][j]
     const bool hi = (pi != i), hj = (pj != j);
-    const double y1r = Yr[i * n + j], y2r = Yr[pi * n + j], y2i = Yi[pi * n + j];
-    const double y3r = Yr[i * n + pj], y3i = Yi[i * n + pj], y4r = Yr[pi * n + pj], y4i = Yi[pi * n + pj];
-    const double tjr = ai_r * y1r + (hi ? (ap_r * y2r - ap_i * y2i) : 0.0);
-    const double tpr = ai_r * y3r + (hi ? (ap_r * y4r - ap_i * y4i) : 0.0), tpi = ai_r * y3i + (hi ? (ap_r * y4i + ap_i * y4r) : 0.0);
+    const auto y1 = BDF_LD2(Y + 2 * (i * n + j)), y2 = BDF_LD2(Y + 2 * (pi * n + j));
+    const auto y3 = BDF_LD2(Y + 2 * (i * n + pj)), y4 = BDF_LD2(Y + 2 * (pi * n + pj));
+    const double tjr = ai_r * y1.x + (hi ? (ap_r * y2.x - ap_i * y2.y) : 0.0);
+    const double tpr = ai_r * y3.x + (hi ? (ap_r * y4.x - ap_i * y4.y) : 0.0), tpi = ai_r * y3.y + (hi ? (ap_r * y4.y + ap_i * y4.x) : 0.0);
     return tjr * bj_r + (hj ? (tpr * bp_r - tpi * bp_i) : 0.0);
 }
 
-// scipy's "LU" event for a new c: reciprocals of the Lyapunov pivots and (I + c L)^{-1} = Q Re(G^H (I + cT)^{-1} G) Q'
+// scipy's "LU" event for a new c: the Lyapunov pivots of the sweep and (I + c L)^{-1} by Gauss-Jordan elimination with partial
+// pivoting on [I + cL | I]: lane c < n owns column c of the left half, lane 16 + c column c of the right half.
 CPDP_D_NOINLINE bool bdf_factor(const double c) {
     BDF_SM();
     constexpr int n = NX;
     const int lane = threadIdx.x;
-    const bool isP = lane < n;
-    const int j = isP ? lane : 0;
-    const double* Tr = sm + bo::TR; const double* Ti = sm + bo::TI; const double* rot = sm + bo::ROT;
-    double* Sr = sm + bo::YR; double* Si = sm + bo::YI;               // S = (I + cT)^{-1}, row stride n (sweep arrays are free here)
+    const bool isP = lane < n, isB = (lane >= 16) && (lane < 16 + n);
+    const double* TD = sm + bo::TD;
+    double* XA = sm + bo::XA; double* XB = sm + bo::XB;
     BDF_SYNC();
     double bad = 0.0;
     if (isP) {
-        const double dr = 1.0 + c * Tr[j * n + j], di = c * Ti[j * n + j];
-        const double dd = dr * dr + di * di;
-        if (!(dd > 0.0)) bad = 1.0;
-        sm[bo::SD + j] = dr / dd; sm[bo::SD + n + j] = -di / dd;
+        const int j = lane;
+        const auto tj = BDF_LD2(TD + 2 * j);
         CPDP_LOOP for (int i = 0; i <= j; ++i) {                 // 1 / ((1/2 + c t_ii) + conj(1/2 + c t_jj))
-            const double er = 1.0 + c * (Tr[i * n + i] + Tr[j * n + j]), ei = c * (Ti[i * n + i] - Ti[j * n + j]);
+            const auto ti = BDF_LD2(TD + 2 * i);
+            const double er = 1.0 + c * (ti.x + tj.x), ei = c * (ti.y - tj.y);
             const double ee = er * er + ei * ei;
             if (!(ee > 0.0)) bad = 1.0;
-            sm[bo::DR + i * n + j] = er / ee; sm[bo::DI + i * n + j] = -ei / ee;
+            const double ie = 1.0 / ee;
+            BDF_ST2(sm + bo::PV + 2 * (i * n + j), er * ie, -ei * ie);
         }
+        BDF_UNROLL for (int i = 0; i < n; ++i) XA[i * NCS + j] = ((i == j) ? 1.0 : 0.0) + c * sm[bo::LM + i * n + j];
+    } else if (isB) {
+        BDF_UNROLL for (int i = 0; i < n; ++i) XB[i * NCS + lane - 16] = (i == lane - 16) ? 1.0 : 0.0;
+    }
+    double* mine = isP ? XA + lane : XB + (isB ? lane - 16 : 0);
+    const bool own = isP || isB;
+    BDF_SYNC();
+    CPDP_LOOP for (int k = 0; k < n; ++k) {
+        const int p = bdf_argmax(sm, (isP && lane >= k) ? XA[lane * NCS + k] : 0.0, isP && lane >= k);     // lane = candidate row
+        if (p < 0) { bad = 1.0; break; }                         // (uniform)
+        if (own && p != k) { const double a = mine[k * NCS], b = mine[p * NCS]; mine[k * NCS] = b; mine[p * NCS] = a; }
+        BDF_SYNC();
+        double ak[n];
+        BDF_UNROLL for (int i = 0; i < n; ++i) ak[i] = XA[i * NCS + k];
+        double piv = 0.0;
+        BDF_UNROLL for (int i = 0; i < n; ++i) if (i == k) piv = ak[i];
+        const double ip = 1.0 / piv;
+        BDF_SYNC();
+        if (own) {
+            double col[n];
+            BDF_UNROLL for (int i = 0; i < n; ++i) col[i] = mine[i * NCS];
+            double ck = 0.0;
+            BDF_UNROLL for (int i = 0; i < n; ++i) if (i == k) ck = col[i];
+            const double t = ck * ip;
+            BDF_UNROLL for (int i = 0; i < n; ++i) mine[i * NCS] = (i == k) ? t : col[i] - ak[i] * t;
+        }
+        BDF_SYNC();
     }
     bad = bdf_reduce(bad, true);
-    BDF_SYNC();
     if (bad != 0.0) return false;
-    if (isP) {                                                   // column j of S (upper triangular) by back substitution
-        CPDP_LOOP for (int i = n - 1; i > j; --i) { Sr[i * n + j] = 0.0; Si[i * n + j] = 0.0; }
-        CPDP_LOOP for (int i = j; i >= 0; --i) {
-            double nr = (i == j) ? 1.0 : 0.0, ni = 0.0;
-            CPDP_LOOP for (int k = i + 1; k <= j; ++k) {
-                const double tr = c * Tr[i * n + k], ti = c * Ti[i * n + k];
-                const double sr = Sr[k * n + j], si = Si[k * n + j];
-                nr -= tr * sr - ti * si;
-                ni -= tr * si + ti * sr;
-            }
-            const double idr = sm[bo::SD + i], idi = sm[bo::SD + n + i];
-            Sr[i * n + j] = nr * idr - ni * idi;
-            Si[i * n + j] = nr * idi + ni * idr;
-        }
-    }
-    BDF_SYNC();
-    if (isP) {                                                   // column j of Re(G^H S G) -> XA
-        CPDP_LOOP for (int i = 0; i < n; ++i) sm[bo::XA + i * NCS + j] = bdf_stencil_GhYG(rot, Sr, Si, i, j);
-    }
-    double t1[n];
-    if (isP) bdf_lmul_k(sm + bo::QT, sm + bo::XA + j, NCS, t1);  // (Q Sr)[:, j]      (own column: no barrier needed)
-    BDF_SYNC();
-    if (isP) bdf_put(sm + bo::XB, j, t1);
-    BDF_SYNC();
-    if (isP) {
-        bdf_lmul_k(sm + bo::QT, sm + bo::XB + j * NCS, 1, t1);   // Q (row j of Q Sr)' = row j of Winv = Q Sr Q'
-        BDF_UNROLL for (int i = 0; i < n; ++i) sm[bo::WT + i * QS + j] = t1[i];      // WT[k][i] = Winv[i][k]
-    }
+    if (isB) { BDF_UNROLL for (int i = 0; i < n; ++i) sm[bo::WT + (lane - 16) * QS + i] = XB[i * NCS + lane - 16]; }     // WT[k][i] = Winv[i][k]
     BDF_SYNC();
     return true;
 }
 
-// Lyapunov sweep  (1/2 + cT) Y + Y (1/2 + cT)^H = C  along anti-diagonals i + j = d (4 lanes per entry); C in (YR, YI)
-// upper triangle, Y overwrites it, both triangles are kept (Y is Hermitian)
+// Lyapunov sweep  (1/2 + cT) Y + Y (1/2 + cT)^H = C  along anti-diagonals i + j = d, four lanes per entry.  C in Y2 (upper
+// triangle), Y overwrites it, both triangles are kept (Y is Hermitian), so both sums of an entry have one form:
+//   Y_ij / pivot_ij = C_ij - c ( S(i, j) + conj S(j, i) ),     S(r, s) = sum_{k > r} T_rk Y_ks .
+// T is stored skewed (T2S[r][t] = T[r][r+1+t], zero beyond the matrix): every lane runs the same SWQ unconditional complex
+// multiply-adds per sum at constant offsets from two base addresses; terms past the matrix multiply a stored zero (the Y
+// operand of such a term may lie past Y2, inside T2S: finite).
 CPDP_D void bdf_sweep(double* sm, const double c) {
     constexpr int n = NX;
     const int tid = threadIdx.x;
-    const double* Tr = sm + bo::TR; const double* Ti = sm + bo::TI;
-    double* Gr = sm + bo::YR; double* Gi = sm + bo::YI;
-    const double* Dr = sm + bo::DR; const double* Di = sm + bo::DI;
+    const double* T2 = sm + bo::T2S; double* Y = sm + bo::Y2; const double* PVm = sm + bo::PV;
     const int e = tid >> 2, sub = tid & 3;
     CPDP_LOOP for (int d = 2 * (n - 1); d >= 0; --d) {
         const int ilo = (d > n - 1) ? d - (n - 1) : 0;
         const int i = ilo + e, j = d - i;
         const bool valid = (i <= j);
-        double ar = 0.0, ai = 0.0;
-        {
-            // every lane issues the same unconditional (index-clamped) loads, out-of-range terms are zeroed by a
-            // select: no branches, all loads in flight together, one short DFMA chain per term
-            constexpr int Mq = (n + 2) / 4;
-            const int ic = valid ? i : 0, jc = valid ? j : 0;
-            double pr[2 * Mq], pi_[2 * Mq];
-            BDF_UNROLL for (int m = 0; m < Mq; ++m) {                                      // T_ik Y_kj,  k = i + 1 + sub + 4 m
-                const int k = ic + 1 + sub + 4 * m;
-                const bool in = valid && (k < n);
-                const int kc = in ? k : 0;
-                const double tr = Tr[ic * n + kc], ti = Ti[ic * n + kc], yr = Gr[kc * n + jc], yi = Gi[kc * n + jc];
-                const double vr = tr * yr - ti * yi, vi = tr * yi + ti * yr;
-                pr[m] = in ? vr : 0.0; pi_[m] = in ? vi : 0.0;
-            }
-            BDF_UNROLL for (int m = 0; m < Mq; ++m) {                                      // Y_ik conj(T_jk),  k = j + 1 + sub + 4 m
-                const int k = jc + 1 + sub + 4 * m;
-                const bool in = valid && (k < n);
-                const int kc = in ? k : 0;
-                const double tr = Tr[jc * n + kc], ti = Ti[jc * n + kc], yr = Gr[ic * n + kc], yi = Gi[ic * n + kc];
-                const double vr = yr * tr + yi * ti, vi = yi * tr - yr * ti;
-                pr[Mq + m] = in ? vr : 0.0; pi_[Mq + m] = in ? vi : 0.0;
-            }
-            BDF_UNROLL for (int m = 0; m < 2 * Mq; ++m) { ar += pr[m]; ai += pi_[m]; }
+        const int ic = valid ? i : 0, jc = valid ? j : 0;
+        const double* ta = T2 + 2 * (ic * TW + sub); const double* ya = Y + 2 * ((ic + 1 + sub) * n + jc);
+        const double* tb = T2 + 2 * (jc * TW + sub); const double* yb = Y + 2 * ((jc + 1 + sub) * n + ic);
+        double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;
+        BDF_UNROLL for (int m = 0; m < SWQ; ++m) {
+            const auto t1 = BDF_LD2(ta + 8 * m), y1 = BDF_LD2(ya + 8 * m * n);
+            const auto t2 = BDF_LD2(tb + 8 * m), y2 = BDF_LD2(yb + 8 * m * n);
+            ar += t1.x * y1.x - t1.y * y1.y; ai += t1.x * y1.y + t1.y * y1.x;
+            br += t2.x * y2.x - t2.y * y2.y; bi += t2.x * y2.y + t2.y * y2.x;
         }
+        ar += br; ai -= bi;
 #ifdef __CUDACC__
         ar += __shfl_xor_sync(0xffffffffu, ar, 1); ai += __shfl_xor_sync(0xffffffffu, ai, 1);
         ar += __shfl_xor_sync(0xffffffffu, ar, 2); ai += __shfl_xor_sync(0xffffffffu, ai, 2);
@@ -694,10 +746,11 @@ CPDP_D void bdf_sweep(double* sm, const double c) {
         }
 #endif
         if (valid && sub == 0) {
-            const double rr = Gr[i * n + j] - c * ar, ri = Gi[i * n + j] - c * ai;
-            const double yr = rr * Dr[i * n + j] - ri * Di[i * n + j], yi = rr * Di[i * n + j] + ri * Dr[i * n + j];
-            Gr[i * n + j] = yr; Gi[i * n + j] = (i == j) ? 0.0 : yi;
-            if (i != j) { Gr[j * n + i] = yr; Gi[j * n + i] = -yi; }
+            const auto cv = BDF_LD2(Y + 2 * (i * n + j)), pv = BDF_LD2(PVm + 2 * (i * n + j));
+            const double rr = cv.x - c * ar, ri = cv.y - c * ai;
+            const double yr = rr * pv.x - ri * pv.y, yi = rr * pv.y + ri * pv.x;
+            BDF_ST2(Y + 2 * (i * n + j), yr, (i == j) ? 0.0 : yi);
+            if (i != j) BDF_ST2(Y + 2 * (j * n + i), yr, -yi);
         }
         BDF_SYNC();
     }
@@ -705,62 +758,67 @@ CPDP_D void bdf_sweep(double* sm, const double c) {
 
 // r <- (I - cJ)^{-1} r   (r: my register column; right-hand side on entry, Newton correction on exit).  Between the stages
 // the columns travel through the exchange buffers, so every product reads its operand vector from shared memory.
-CPDP_D void bdf_solve_cols(double* sm, const double c, double (&r)[NX]) {
+CPDP_D void bdf_solve_cols(double* sm, const double c, double (&r)[NX] BDF_TP_PARAM) {
     constexpr int n = NX;
     const int lane = threadIdx.x;
     const bool isP = lane < n, isW = (lane >= n) && (lane < NC);
     const int j = isP ? lane : 0;
     const double* rot = sm + bo::ROT;
-    double t1[n];
-    if (isP) {
-        bdf_put(sm + bo::XA, j, r);
-        bdf_lmul_k(sm + bo::Q, sm + bo::XA + j, NCS, t1);        // (Q'B)[:, j]
-    }
+    double* XA = sm + bo::XA; double* XB = sm + bo::XB;
+    int hc, hi0;
+    const bool hact = bdf_half(lane, hc, hi0);                   // products: lanes c and 16 + c share column c
+    BDF_T(10, {
+    if (isP) bdf_put(XA, j, r);
     BDF_SYNC();
-    if (isP) bdf_put(sm + bo::XB, j, t1);
+    if (hact) bdf_lmul_to(sm + bo::Q, QS, XA + hc, NCS, XB + hc, NCS, hi0);        // (Q'B)[:, c]
     BDF_SYNC();
-    if (isP) bdf_lmul_k(sm + bo::Q, sm + bo::XB + j * NCS, 1, t1);      // Q'(row j of Q'B)' = row j (= column j) of E = Q'BQ
+    if (hact) bdf_lmul_to(sm + bo::Q, QS, XB + hc * NCS, 1, XA + hc, NCS, hi0);    // Q'(row c of Q'B)' = row c (= column c) of E = Q'BQ
     BDF_SYNC();
-    if (isP) bdf_put(sm + bo::XA, j, t1);
-    BDF_SYNC();
-    if (isP) {                                                   // C = G E G^H, upper triangle of my column -> sweep arrays
-        CPDP_LOOP for (int i = 0; i <= j; ++i) {
+    });
+    BDF_T(11, {
+    if (isP) {                                                   // C = G E G^H, upper triangle of my column -> sweep array
+        BDF_PRAGMA_UNROLL(CPDP_BDF_STENCIL_UNROLL) for (int i = 0; i <= j; ++i) {
             double cr, ci;
-            bdf_stencil_GEGh(rot, sm + bo::XA, NCS, i, j, cr, ci);
-            sm[bo::YR + i * n + j] = cr; sm[bo::YI + i * n + j] = ci;
+            bdf_stencil_GEGh(rot, XA, NCS, i, j, cr, ci);
+            BDF_ST2(sm + bo::Y2 + 2 * (i * n + j), cr, ci);
         }
     }
     BDF_SYNC();
-    bdf_sweep(sm, c);
-    BDF_SYNC();
+    });
+    BDF_T(12, { bdf_sweep(sm, c); BDF_SYNC(); });
+    BDF_T(13, {
     if (isP) {                                                   // Yr = Re(G^H Y G), my column -> XA
-        CPDP_LOOP for (int i = 0; i < n; ++i) sm[bo::XA + i * NCS + j] = bdf_stencil_GhYG(rot, sm + bo::YR, sm + bo::YI, i, j);
-        bdf_lmul_k(sm + bo::QT, sm + bo::XA + j, NCS, t1);       // (Q Yr)[:, j]
+        BDF_PRAGMA_UNROLL(CPDP_BDF_STENCIL_UNROLL) for (int i = 0; i < n; ++i) XA[i * NCS + j] = bdf_stencil_GhYG(rot, sm + bo::Y2, i, j);
     }
     BDF_SYNC();
-    if (isP) bdf_put(sm + bo::XB, j, t1);
+    });
+    BDF_T(14, {
+    if (hact) bdf_lmul_to(sm + bo::QT, QS, XA + hc, NCS, XB + hc, NCS, hi0);       // (Q Yr)[:, c]
     BDF_SYNC();
-    if (isP) bdf_lmul_k(sm + bo::QT, sm + bo::XB + j * NCS, 1, t1);     // row j of X = Q Yr Q'
+    if (hact) bdf_lmul_to(sm + bo::QT, QS, XB + hc * NCS, 1, XA + hc, NCS, hi0);   // row c of X = Q Yr Q':  XA[i][c] = X[c][i]
     BDF_SYNC();
-    if (isP) bdf_put(sm + bo::XA, j, t1);                        // XA[i][j] = X[j][i]
+    });
+    BDF_T(15, {
+    double xs_[NX];
+    if (isP) { BDF_UNROLL for (int i = 0; i < n; ++i) xs_[i] = 0.5 * (XA[i * NCS + j] + XA[j * NCS + i]); }   // X <- (X + X') / 2
     BDF_SYNC();
-    if (isP) {                                                   // X <- (X + X') / 2: bitwise symmetric
-        BDF_UNROLL for (int i = 0; i < n; ++i) r[i] = 0.5 * (t1[i] + sm[bo::XA + j * NCS + i]);
-        bdf_put(sm + bo::XB, j, r);
-        double xc[NP];                                           // row j of X C  (X symmetric: X[j][a] = my column)
-        BDF_UNROLL for (int q = 0; q < NP; ++q) xc[q] = 0.0;
-        CPDP_LOOP for (int a = 0; a < n; ++a) {
-            const double xa = sm[bo::XB + a * NCS + j];
-            BDF_UNROLL for (int q = 0; q < NP; ++q) xc[q] += xa * sm[bo::CM + a * NP + q];
-        }
-        BDF_UNROLL for (int q = 0; q < NP; ++q) sm[bo::XA + j * NCS + n + q] = xc[q];
+    if (isP) {
+        BDF_UNROLL for (int i = 0; i < n; ++i) r[i] = xs_[i];
+        bdf_put(XA, j, r);                                       // XA = X, bitwise symmetric
     }
     BDF_SYNC();
-    if (isW) {                                                   // dW = (I + cL)^{-1} (B_W + c X C)
-        BDF_UNROLL for (int i = 0; i < n; ++i) sm[bo::XB + i * NCS + lane] = r[i] + c * sm[bo::XA + i * NCS + lane];
-        bdf_lmul_k(sm + bo::WT, sm + bo::XB + lane, NCS, r);
-    }
+    // dW = (I + cL)^{-1} (B_W + c X C), two lanes per W column.  (X C)[:, k] = X C[:, k]: X is symmetric, so X itself (XA,
+    // row stride NCS) is the k-major operand of the product
+    const int wc = lane & 15, wi0 = (lane >> 4) ? NX - NH : 0;
+    if (wc < NP) bdf_lmul_to(XA, NCS, sm + bo::CM + wc, NP, XB + n + wc, NCS, wi0);
     BDF_SYNC();
+    if (isW) { BDF_UNROLL for (int i = 0; i < n; ++i) XB[i * NCS + lane] = r[i] + c * XB[i * NCS + lane]; }
+    BDF_SYNC();
+    if (wc < NP) bdf_lmul_to(sm + bo::WT, QS, XB + n + wc, NCS, XA + n + wc, NCS, wi0);
+    BDF_SYNC();
+    if (isW) { BDF_UNROLL for (int i = 0; i < n; ++i) r[i] = XA[i * NCS + lane]; }
+    BDF_SYNC();
+    });
 }
 
 // change_D (bdf.py:18-33): D[:order+1] <- (R U)' D[:order+1]   (D in the global workspace, [row][i][lane])
@@ -818,31 +876,18 @@ CPDP_D_NOINLINE double bdf_norm_row(const double* Drow, const double* iscm, cons
     return sqrt(bdf_reduce(a, false) / (double)NFULL_R);
 }
 
-// out-of-line right-hand side for the (cold) start-up of an interval: columns through shared memory (XA in, XA out)
-CPDP_D_NOINLINE void bdf_rhs_smem() {
+// The one out-of-line instance of the right-hand side: state columns in through XB, derivative columns out through XB.
+// sym: bitwise symmetric P block (start-up of an interval, where the value seeds the differences array).
+CPDP_D_NOINLINE void bdf_rhs_smem(const bool sym) {
     BDF_SM();
     const int c = threadIdx.x < NC ? threadIdx.x : 0;
     double y[NX], f[NX];
-    bdf_get_col(sm + bo::XA, c, y);
+    bdf_get_col(sm + bo::XB, c, y);
     BDF_SYNC();
-    bdf_rhs_cols<true>(sm, y, f);
-    if (threadIdx.x < NC) bdf_put(sm + bo::XA, c, f);
+    bdf_rhs_cols(sm, y, f, sym);
+    if (threadIdx.x < NC) bdf_put(sm + bo::XB, c, f);
     BDF_SYNC();
 }
-
-// Developer instrumentation (-DCPDP_BDF_TIMING): per-phase clock64() totals of each problem, written over the Ua rows of
-// the problem at kernel end (phases = 1 runs only; tools/prof_bdf_phases.py).  Off in the shipped library.
-#ifdef CPDP_BDF_TIMING
-#define BDF_T(ph, expr) do { const long long t0__ = clock64(); expr; tp[ph] += clock64() - t0__; } while (0)
-#define BDF_TB(ph, var, expr) do { const long long t0__ = clock64(); var = (expr); tp[ph] += clock64() - t0__; } while (0)
-#define BDF_TP_PARAM , long long* tp
-#define BDF_TP_ARG , tp
-#else
-#define BDF_T(ph, expr) do { expr; } while (0)
-#define BDF_TB(ph, var, expr) do { var = (expr); } while (0)
-#define BDF_TP_PARAM
-#define BDF_TP_ARG
-#endif
 
 // One grid interval [t0, t1] with scipy's BDF.  y: state columns in registers (in/out).  Returns 0 ok, 1 step too small,
 // 2 non-finite, 4 singular Newton matrix.  cnt: [rhs evaluations, steps (accepted), LU factorisations, Jacobians]
@@ -860,10 +905,10 @@ CPDP_D int bdf_interval(double* sm, double* D, const AuxProblem& p, const double
     if (act) bdf_put(sm + bo::XA, lc, y);
     BDF_SYNC();
     BDF_T(2, bdf_jacobian()); ++cnt[3];                                  // reads the state columns from XA
-    if (act) bdf_put(sm + bo::XA, lc, y);
+    if (act) bdf_put(sm + bo::XB, lc, y);
     BDF_SYNC();
-    BDF_T(1, bdf_rhs_smem()); ++cnt[0];
-    bdf_get_col(sm + bo::XA, lc, f0);
+    BDF_T(1, bdf_rhs_smem(true)); ++cnt[0];
+    bdf_get_col(sm + bo::XB, lc, f0);
     BDF_SYNC();
     { bool oks__; BDF_TB(3, oks__, bdf_schur()); if (!oks__) return 4; }
     double h_abs;
@@ -883,10 +928,10 @@ CPDP_D int bdf_interval(double* sm, double* D, const AuxProblem& p, const double
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         h0 = fmin(h0, interval_length);
         double f1[NX];
-        if (act) { BDF_UNROLL for (int i = 0; i < NX; ++i) f1[i] = y[i] + h0 * dir * f0[i]; bdf_put(sm + bo::XA, lc, f1); }
+        if (act) { BDF_UNROLL for (int i = 0; i < NX; ++i) f1[i] = y[i] + h0 * dir * f0[i]; bdf_put(sm + bo::XB, lc, f1); }
         { bool okp__; BDF_TB(0, okp__, bdf_prepare(p, t0 + h0 * dir)); if (!okp__) return 2; }
-        BDF_T(1, bdf_rhs_smem()); ++cnt[0];
-        bdf_get_col(sm + bo::XA, lc, f1);
+        BDF_T(1, bdf_rhs_smem(true)); ++cnt[0];
+        bdf_get_col(sm + bo::XB, lc, f1);
         BDF_SYNC();
         double a2 = 0.0;
         if (act) {
@@ -938,11 +983,10 @@ CPDP_D int bdf_interval(double* sm, double* D, const AuxProblem& p, const double
             if (act) {
                 double dk[NX];
                 BDF_UNROLL for (int i = 0; i < NX; ++i) { y[i] = 0.0; psi[i] = 0.0; }
-                BDF_UNROLL for (int k = 0; k <= BDF_MAX_ORDER; ++k) {
-                    if (k <= order) {
-                        BDF_UNROLL for (int i = 0; i < NX; ++i) dk[i] = D_(k, i);
-                        BDF_UNROLL for (int i = 0; i < NX; ++i) { y[i] += dk[i]; if (k >= 1) psi[i] += dk[i] * bdf_gamma(k); }
-                    }
+                CPDP_LOOP for (int k = 0; k <= order; ++k) {
+                    const double gk = bdf_gamma(k);                          // gamma_0 = 0: psi += 0 * D[0] adds an exact zero
+                    BDF_UNROLL for (int i = 0; i < NX; ++i) dk[i] = D_(k, i);
+                    BDF_UNROLL for (int i = 0; i < NX; ++i) { y[i] += dk[i]; psi[i] += dk[i] * gk; }
                 }
                 BDF_UNROLL for (int i = 0; i < NX; ++i) {                // y = y_predict: the Newton iteration starts from it
                     isc[i] = bdf_rcp(atol + rtol * fabs(y[i]));
@@ -963,7 +1007,10 @@ CPDP_D int bdf_interval(double* sm, double* D, const AuxProblem& p, const double
                 int k = 0;
                 CPDP_LOOP for (k = 0; k < BDF_NEWTON_MAXITER; ++k) {
                     double r[NX];
-                    BDF_T(1, bdf_rhs_cols<false>(sm, y, r)); ++cnt[0];
+                    if (act) bdf_put(sm + bo::XB, lc, y);
+                    BDF_SYNC();
+                    BDF_T(1, bdf_rhs_smem(false)); ++cnt[0];
+                    bdf_get_col(sm + bo::XB, lc, r);
                     double fin = 0.0;
                     BDF_UNROLL for (int i = 0; i < NX; ++i) {
                         if (act && !(fabs(r[i]) < 1e300)) fin = 1.0;
@@ -971,7 +1018,7 @@ CPDP_D int bdf_interval(double* sm, double* D, const AuxProblem& p, const double
                     }
                     fin = bdf_reduce(fin, true);
                     if (fin != 0.0) break;
-                    BDF_T(5, bdf_solve_cols(sm, c_lu, r));
+                    BDF_T(5, bdf_solve_cols(sm, c_lu, r BDF_TP_ARG));
                     double dy_norm; BDF_TB(6, dy_norm, bdf_norm_cols(r, isc, 1.0, act));
                     const bool have_rate = dy_norm_old >= 0.0;
                     const double rate = have_rate ? dy_norm / dy_norm_old : 0.0;
@@ -1075,7 +1122,7 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, CPDP_BDF_MINB) k_riccati_bdf(Aux
     p.X = a.X + (size_t)b * (N + 1) * NX; p.U = a.U + (size_t)b * (N + 1) * NU; p.Lam = a.Lam + (size_t)b * (N + 1) * NX;
     p.th = a.theta + (size_t)b * a.theta_stride; p.pd = a.pdata + (size_t)b * NQ; p.PW = nullptr; p.dt = a.T / N; p.N = N;
     double* PW = a.PW + (size_t)b * (N + 1) * NYR;
-    double* s_hxx = sm + bo::YR; double* s_hxe = sm + bo::XA;     // terminal condition staged in scratch (NX*NX and NX*NP doubles)
+    double* s_hxx = sm + bo::PV; double* s_hxe = sm + bo::XA;     // terminal condition staged in scratch (NX*NX and NX*NP doubles)
     if (lane == 0) {
         const double tN = p.dt * N;
         double xT[NX];
@@ -1101,7 +1148,7 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, CPDP_BDF_MINB) k_riccati_bdf(Aux
     int cnt[4] = {0, 0, 0, 0};
     int st = 0;
 #ifdef CPDP_BDF_TIMING
-    long long tp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tp[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long tstart__ = clock64();
 #endif
     CPDP_LOOP for (int k = N; k >= 1 && st == 0; --k) {
@@ -1114,7 +1161,7 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, CPDP_BDF_MINB) k_riccati_bdf(Aux
     if (lane == 0) {
         tp[8] = clock64() - tstart__;
         double* dst = a.Ua + (size_t)b * (N + 1) * NU * NP;
-        for (int i = 0; i < 10; ++i) dst[i] = (double)tp[i];
+        for (int i = 0; i < 16; ++i) dst[i] = (double)tp[i];
     }
 #endif
     if (lane == 0) {

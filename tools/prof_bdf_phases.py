@@ -18,8 +18,10 @@ sys.path.insert(0, ROOT)
 VARIANTS = {
     "base": [],
     "time": ["-DCPDP_BDF_TIMING"],
-    "minb6": ["-DCPDP_BDF_MINB=6"],
-    "minb10": ["-DCPDP_BDF_MINB=10"],
+    "l2s1": ["-DCPDP_BDF_LMUL_UNROLL=2", "-DCPDP_BDF_STENCIL_UNROLL=1"],
+    "l1s1": ["-DCPDP_BDF_LMUL_UNROLL=1", "-DCPDP_BDF_STENCIL_UNROLL=1"],
+    "l4s2": ["-DCPDP_BDF_LMUL_UNROLL=4", "-DCPDP_BDF_STENCIL_UNROLL=2"],
+    "l13s1": ["-DCPDP_BDF_LMUL_UNROLL=13", "-DCPDP_BDF_STENCIL_UNROLL=1"],
 }
 PHASES = ["prepare", "rhs", "jacobian", "schur", "factor", "solve", "norm", "change_D", "total"]
 
@@ -70,7 +72,7 @@ def main():
             out = {"variant": v, "batch": B, "ms": [round(t, 3) for t in times],
                    "failed": int((aux["aux_status"] != 0).sum().item())}
             if "time" in v:
-                tp = aux["Ua"].reshape(B, -1)[:, :10].cpu().numpy()
+                tp = aux["Ua"].reshape(B, -1)[:, :16].cpu().numpy()
                 tot = tp[:, 8].mean()
                 out["cycles_total_mean"] = float(tot)
                 out["phase_share"] = {PHASES[i]: round(float(tp[:, i].mean() / tot), 4) for i in range(8)}
@@ -84,6 +86,9 @@ def main():
                     "factor": float(tp[:, 4].mean() / cnt[:, 4].mean()),
                     "solve": float(tp[:, 5].mean() / (cnt[:, 0].mean() - 2 * a.n_grid)),
                 }
+                nsol = cnt[:, 0].mean() - 2 * a.n_grid
+                out["solve_cycles_per_call"] = {nm: float(tp[:, 10 + i].mean() / nsol) for i, nm in enumerate(
+                    ["QtBQ", "stencil_in", "sweep", "stencil_out", "QYQt", "sym_W"])}
             print(json.dumps(out), flush=True)
 
 
