@@ -25,6 +25,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "CPDP OCP gradient-iterations per second (batched quadrotor OCPs, n_grid 50)"
+PORT_S_PER_OCP = 2.0      # core-seconds per OCP of the CPU port on the GPU boxes' host cores (measured; sizes the reference arm)
 UNIT = "ocp_grad_iters/s"
 
 
@@ -76,7 +77,9 @@ def _cpu_one(job):
     x0, goal, theta, taus, wp = job
     _ORC.pd = goal
     t0 = time.time()
-    loss, dl, ex = _ORC.grad_iter(x0, 1.0, theta, taus, wp)       # as-shipped: BDF backward, RK45 forward
+    # as shipped: BDF backward, RK45 forward (scipy's own solve_ivp); Newton steps through the stage-structured (Riccati)
+    # factorisation of the KKT matrix, so the port is not charged for a dense factorisation no sparse NLP solver performs
+    loss, dl, ex = _ORC.grad_iter(x0, 1.0, theta, taus, wp, linear_solver="riccati")
     return loss, dl, ex["info"]["iters"], time.time() - t0
 
 
@@ -117,10 +120,12 @@ def cpu_baseline(n_grid, sample, steps=1, warmup=0, max_workers=0, deadline_s=24
                 break
         dt = time.time() - t0
     value = sample * done / dt
-    return dict(value=value, unit=UNIT, cores=workers, kind="port",
+    return dict(value=value, unit=UNIT, cores=workers, kind="port", sample_ocps=sample,
                 sample="%d OCPs per step (first indices of the seeded 4096-OCP batch), n_grid %d, %d step(s), %.1f s wall, "
-                       "%.1f s per OCP per core; oracle = numpy/scipy restatement of the reference algorithm (Newton-KKT in "
-                       "place of IPOPT, scipy BDF/RK45 as shipped), one single-threaded process per host core (%d cores)"
+                       "%.1f s per OCP per core; numpy/scipy port of the reference algorithm (Newton-KKT with a stage-structured "
+                       "factorisation in place of IPOPT/MUMPS, scipy's BDF/RK45 called as shipped, model functions through "
+                       "sympy.lambdify), one single-threaded process per host core (%d cores); its speed relative to the real "
+                       "CasADi VM + IPOPT is unknown"
                        % (sample, n_grid, done, dt, float(np.mean(per)), cores)), dt, done
 
 
@@ -392,10 +397,11 @@ def run_ours(a):
     # (profiles/r01_ncu_<kernel>.json, written by tools/ncu_summary.py); null when no capture of this shape exists.
     traffic, traffic_src = None, None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_%s.json" % kname)))
+        pname = "r02_ncu_%s.json" % kname if os.path.exists(os.path.join(ROOT, "profiles", "r02_ncu_%s.json" % kname)) else "r01_ncu_%s.json" % kname
+        prof = json.load(open(os.path.join(ROOT, "profiles", pname)))
         if prof.get("batch") == Bl and prof.get("n_grid") == a.n_grid:
             traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
-            traffic_src = "profiles/r01_ncu_%s.json" % kname
+            traffic_src = "profiles/" + pname
     except Exception:
         pass
     out = {
@@ -403,7 +409,8 @@ def run_ours(a):
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%d quadrotor OCPs%s (n=13,m=4,r=7), n_grid 50, S=4, T=1, shared theta0, "
-                               "rng default_rng(20210308); SURVEY.md 8d / BASELINE.json configs[4]" % (a.batch, " per GPU" if a.scaling == "weak" else " total"),
+                               "rng default_rng(20210308); SURVEY.md 8d / BASELINE.json configs[4]" % (
+                                   a.batch, " per GPU (weak scaling)" if a.scaling == "weak" else " in total, sharded contiguously over the GPUs (strong scaling)"),
                    "n_grid": a.n_grid, "global_batch": B_total, "aux_mode": mode, "rtol_back": a.rtol, "atol_back": a.atol,
                    "parallelism": "dp%d contiguous shards, all-gather of per-OCP (loss,dtheta) rows + fixed-tree sum" % world,
                    "streams": "%d chunk(s) of each shard on separate CUDA streams, %s" % (
@@ -412,9 +419,9 @@ def run_ours(a):
                          "every step starts from the zero seed" % (lib.workspace_bytes(Bl, a.n_grid, 4) / 1e9)},
         "e2e": {"value": B_total * a.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": (r + 2) * 8},
-        # timed region: per chunk k_solve_init + k_compact + 4 kernels per Newton round + backward + forward sweep, then one
-        # k_reduce_tree (single-stream mode launches only the rounds the adaptive solve needed)
-        "gpu_launches": a.steps * ((a.chunks * (2 + 4 * a.rounds + 2) + 1) if a.chunks > 1 else (2 + 4 * rounds + 2 + 1)),
+        # timed region: per chunk k_solve_init + k_compact + 4 kernels per Newton round + backward + forward sweep, then
+        # k_pack_rows + k_reduce_rows (single-stream mode launches only the rounds the adaptive solve needed)
+        "gpu_launches": a.steps * ((a.chunks * (2 + 4 * a.rounds + 2) + 2) if a.chunks > 1 else (2 + 4 * rounds + 2 + 2)),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "kernel": kname, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic, "traffic_source": traffic_src,
@@ -433,8 +440,11 @@ def run_ours(a):
                   "aux_failed": int(loc[2]), "back_rhs_mean": loc[3] / B_total, "back_steps_mean": loc[4] / B_total,
                   "fwd_rhs_mean": loc[5] / B_total, "fwd_steps_mean": loc[6] / B_total,
                   "back_lu_mean": loc[7] / B_total, "back_jac_mean": loc[8] / B_total,
-                  "loss_sum": float(red[0].item())},
+                  "loss_sum": float(red[0].item()), "failed_ocps_in_reduced_row": int(round(float(red[-1].item())))},
     }
+    # a step that averaged failed problems into its gradient is not a valid measurement (fixed Newton rounds that are too few
+    # would leave problems `running`; the count travels with the reduced row, see cpdp_pack_rows)
+    out["valid"] = (int(loc[1]) == 0 and int(loc[2]) == 0 and out["stats"]["failed_ocps_in_reduced_row"] == 0)
     if world == 1 and not a.no_cpu_baseline:
         cb, _, _ = cpu_baseline(a.n_grid, a.cpu_sample, deadline_s=a.cpu_deadline)
         out["cpu_baseline"] = cb
@@ -448,12 +458,18 @@ def run_reference(a):
     if rank != 0:
         return
     import lfsd_b200  # noqa: F401
-    cb, dt, steps = cpu_baseline(a.n_grid, a.cpu_sample, steps=a.steps, warmup=0, deadline_s=a.cpu_deadline)
+    # every step = a bounded sample of the workload, sized so that --steps of them end within the deadline: the port needs
+    # about PORT_S_PER_OCP core-seconds per OCP, so a step may hold  cores * deadline / (steps * PORT_S_PER_OCP)  OCPs
+    cores = os.cpu_count() or 1
+    sample = a.cpu_sample or max(cores, min(4 * cores, int(cores * 0.8 * a.cpu_deadline / (max(a.steps + a.warmup, 1) * PORT_S_PER_OCP))))
+    cb, dt, steps = cpu_baseline(a.n_grid, sample, steps=a.steps, warmup=0, deadline_s=a.cpu_deadline)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
            "warmup": a.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": a.scaling,
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "%d quadrotor OCPs per step (bounded sample of the 4096-OCP batch), n_grid %d" % (cb["cores"], a.n_grid),
-                      "note": "the reference's CasADi/IPOPT path cannot run in this image (no casadi); this is the CPU oracle port"},
+           "config": {"workload": "%d quadrotor OCPs per step (bounded sample: the first indices of the seeded 4096-OCP batch), n_grid %d"
+                                  % (cb["sample_ocps"], a.n_grid),
+                      "note": "the reference's CasADi/IPOPT path cannot run in this image (no casadi); this is the numpy/scipy port of "
+                              "the same algorithm (kind 'port'): its speed relative to CasADi's C++ VM + IPOPT/MUMPS is unknown"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))

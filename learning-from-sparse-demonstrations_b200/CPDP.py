@@ -16,7 +16,7 @@ from .sx import SX, jacobian
 from . import codegen
 from . import _capi
 
-__all__ = ["COCSys"]
+__all__ = ["COCSys", "COCSys_TimeVarying"]
 
 
 class _TorchCuda:
@@ -204,7 +204,8 @@ class COCSys:
         if self._lib is not None and not force:
             return self._lib
         text, info = codegen.generate_model_header(name or self.sys_name, self.state, self.control, self.auxvar,
-                                                    self.dyn, self.path_cost, self.final_cost, self.pvar)
+                                                    self.dyn, self.path_cost, self.final_cost, self.pvar,
+                                                    time=getattr(self, 'time', None))
         self.codegen_info = info
         libname = name if name is not None else "m" + info["hash"]
         so = _capi.build_model_library(libname, text, force=force, verbose=verbose)
@@ -276,9 +277,14 @@ class COCSys:
                   float(self.tol), int(self.max_iter), int(rounds),
                   mem.ptr(out["X"]), mem.ptr(out["U"]), mem.ptr(out["Lam"]), mem.ptr(out["status"]), mem.ptr(out["iters"]),
                   mem.ptr(out["kkt"]), mem.ptr(out["cost"]), mem.stream())
-        out.update(time_grid=numpy.array([horizon / N * k for k in range(N + 1)]), horizon=float(horizon),
+        out.update(time_grid=self._time_grid(horizon, N), horizon=float(horizon),
                    theta=th, theta_stride=th_stride, pdata=pd, B=B, x0=x0, _slot=_slot)
         return out
+
+    @staticmethod
+    def _time_grid(horizon, N):
+        """CPDP.py:192"""
+        return numpy.array([horizon / N * k for k in range(N + 1)])
 
     def auxSysSolverBatch(self, sol, taus=None, waypoints=None, sel=None, mode=None, phases=3, out=None):
         """Batched auxSysSolver (+ fused loss closure).  ``sol`` is the dict returned by cocSolverBatch.
@@ -478,3 +484,49 @@ class COCSys:
     def interpolation(self, x, y, method=1):
         """CPDP.py:384-390"""
         return _Interp(x, y, method)
+
+
+class COCSys_TimeVarying(COCSys):
+    """Time-varying continuous optimal-control system: dynamics, path cost and final cost may depend on the time ``t``
+    explicitly (polynomial time-warping v(t) = beta1 + 2 beta2 t + ...), mirroring the reference class of the same name
+    (``/root/reference/CPDP/CPDP.py:394-787``; driver ``Examples/pendulum_timewarping.py``).  Differences from COCSys, all the
+    reference's own:
+      * ``setTimeVariable`` (:434); every model function takes the time;
+      * the RK4 interval map freezes ``t = t_k`` over the whole grid interval (:512-519, 554-555) and the grid is
+        ``numpy.linspace(0, horizon, n_grid + 1)`` (:544);
+      * the backward Riccati sweep is integrated by ``solve_ivp``'s default RK45, not BDF (:740) -> ``aux_mode = MODE_RK45``.
+    The kernels are the same ones (``cpdp_solve`` / ``cpdp_aux``): the code generator emits the time as one more model
+    constant that the kernels fill in per node / per stage time."""
+
+    def __init__(self, project_name="myOc"):
+        super().__init__(project_name)
+        self.aux_mode = COCSys.MODE_RK45
+
+    def setTimeVariable(self, t=None):
+        """CPDP.py:434-435"""
+        self.time = SX.sym('time', 1) if t is None else t
+        self._lib = None
+
+    def _ensure_time(self):
+        if not hasattr(self, 'time'):
+            self.setTimeVariable()
+
+    def setDyn(self, ode):
+        """CPDP.py:438-450"""
+        self._ensure_time()
+        super().setDyn(ode)
+
+    def setPathCost(self, path_cost):
+        """CPDP.py:453-466"""
+        self._ensure_time()
+        super().setPathCost(path_cost)
+
+    def setFinalCost(self, final_cost):
+        """CPDP.py:469-478"""
+        self._ensure_time()
+        super().setFinalCost(final_cost)
+
+    @staticmethod
+    def _time_grid(horizon, N):
+        """CPDP.py:544"""
+        return numpy.linspace(0, horizon, N + 1)

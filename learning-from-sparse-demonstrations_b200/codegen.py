@@ -95,13 +95,18 @@ def _sparse_tables(name, M):
                       "    static constexpr int %s_nnz = %d;" % (name, len(colidx))])
 
 
-def generate_model_header(name, state, control, auxvar, dyn, path_cost, final_cost, pdata=None):
+def generate_model_header(name, state, control, auxvar, dyn, path_cost, final_cost, pdata=None, time=None):
     """Returns (header_text, info dict).  All arguments are SX / sympy matrices / scalars.
-    ``pdata``: optional per-problem constants (e.g. a goal position) that are not learnable."""
+    ``pdata``: optional per-problem constants (e.g. a goal position) that are not learnable.
+    ``time``: the explicit time variable of a COCSys_TimeVarying model (CPDP.py:434); the generated functions read it as
+    one more constant, pd[nq], which the kernels fill in (the node time t_k in the RK4 map, the true t in the sweeps)."""
     x, u, th = _vec(state), _vec(control), _vec(auxvar)
     pdv = _vec(pdata) if pdata is not None else []
     n, m, r = len(x), len(u), len(th)
     nq = len(pdv)
+    tv = _vec(time) if time is not None else []
+    assert len(tv) <= 1, "the time variable is a scalar"
+    pdv = pdv + tv                                   # nq stays the number of USER constants; t rides behind them
     # sx.SX.sym is backed by sympy symbols, which are identified by NAME (CasADi's are distinct objects): a name reused across
     # state / control / auxvar / problem constants would silently alias two variables
     allsyms = x + u + th + pdv
@@ -119,7 +124,7 @@ def generate_model_header(name, state, control, auxvar, dyn, path_cost, final_co
     xs = [sp.Symbol("x[%d]" % i, real=True) for i in range(n)]
     us = [sp.Symbol("u[%d]" % i, real=True) for i in range(m)]
     ts = [sp.Symbol("th[%d]" % i, real=True) for i in range(r)]
-    ps = [sp.Symbol("pd[%d]" % i, real=True) for i in range(nq)]
+    ps = [sp.Symbol("pd[%d]" % i, real=True) for i in range(len(pdv))]
     sub = dict(zip(x + u + th + pdv, xs + us + ts + ps))
     f = f.subs(sub); c = c.subs(sub); h = h.subs(sub)
     z = xs + us
@@ -206,11 +211,12 @@ struct Model {{
     static constexpr int NU = {m};
     static constexpr int NP = {r};
     static constexpr int NQ = {nq};
+    static constexpr int HAS_TIME = {has_time};
     static constexpr int NZ = {nz};
 {offs}
 {tables}
 {parts}
 }};
-""".format(name=name, nz=nz, offs="\n".join(offs), tables=tables, parts="\n\n".join(parts), **info)
+""".format(name=name, nz=nz, has_time=len(tv), offs="\n".join(offs), tables=tables, parts="\n\n".join(parts), **info)
     info["hash"] = hashlib.sha1(text.encode()).hexdigest()[:16]
     return text, info

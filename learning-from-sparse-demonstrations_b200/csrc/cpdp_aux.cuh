@@ -163,8 +163,9 @@ CPDP_D double xul_at(const AuxProblem& p, double t, int e) {
     return interp_val(p.Lam[(size_t)lo * NX + e - NX - NU], p.Lam[(size_t)(lo + 1) * NX + e - NX - NU], xlo, xhi, t);
 }
 // PMP matrices + inv(Huu) of one slot from its interpolated (x, u, lam); executed by ONE thread
-CPDP_D bool pmp_eval(const AuxProblem& p, const double* xul, double* M) {
-    Model::pmp(xul, xul + NX, xul + NX + NU, p.th, p.pd, M);
+CPDP_D bool pmp_eval(const AuxProblem& p, const double* xul, double* M, const double t) {
+    PdBuf pdb;
+    Model::pmp(xul, xul + NX, xul + NX + NU, p.th, pd_at(p.pd, t, pdb), M);
     if (Model::HUU_DIAG) {           // every JinEnv model: Huu = diag (control-effort weights); the general inverse stays for user models
         bool ok = true;
         double* Hi = M + Model::PMP_SIZE;
@@ -306,7 +307,7 @@ CPDP_D bool aux_prepare(const AuxShared& s, const AuxProblem& p, const double* t
     }
     __syncthreads();
     if (tid < cnt) {
-        if (!pmp_eval(p, s.xul + (size_t)tid * (2 * NX + NU), s.M + (size_t)tid * MSZ)) bad = 1.0;
+        if (!pmp_eval(p, s.xul + (size_t)tid * (2 * NX + NU), s.M + (size_t)tid * MSZ, times[tid])) bad = 1.0;
     }
     if (FWD) {
         CPDP_LOOP for (int q = tid; q < cnt * NYR; q += nt) {
@@ -596,7 +597,8 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
         double xT[NX];
         const int lo = interp_lo(tN, p.dt, N);
         for (int i = 0; i < NX; ++i) xT[i] = interp_val(p.X[(size_t)lo * NX + i], p.X[(size_t)(lo + 1) * NX + i], p.dt * lo, p.dt * (lo + 1), tN);
-        Model::term2(xT, p.th, p.pd, s_hxx, s_hxe);
+        PdBuf pdb;
+        Model::term2(xT, p.th, pd_at(p.pd, tN, pdb), s_hxx, s_hxe);
     }
     __syncthreads();
     for (int q = tid; q < NYR; q += nt) {

@@ -206,7 +206,7 @@ CPDP_D_NOINLINE bool bdf_prepare(const AuxProblem p, const double t) {
     CPDP_LOOP for (int q = lane; q < 2 * NX + NU; q += BDF_THREADS) sm[bo::XUL + q] = xul_at(p, t, q);
     BDF_SYNC();
     int* flag = (int*)(sm + bo::FLAG);
-    if (lane == 0) flag[0] = pmp_eval(p, sm + bo::XUL, sm + bo::M) ? 1 : 0;
+    if (lane == 0) flag[0] = pmp_eval(p, sm + bo::XUL, sm + bo::M, t) ? 1 : 0;
     BDF_SYNC();
     return flag[0] != 0;
 }
@@ -1128,7 +1128,8 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, CPDP_BDF_MINB) k_riccati_bdf(Aux
         double xT[NX];
         const int lo = interp_lo(tN, p.dt, N);
         CPDP_LOOP for (int i = 0; i < NX; ++i) xT[i] = interp_val(p.X[(size_t)lo * NX + i], p.X[(size_t)(lo + 1) * NX + i], p.dt * lo, p.dt * (lo + 1), tN);
-        Model::term2(xT, p.th, p.pd, s_hxx, s_hxe);
+        PdBuf pdb;
+        Model::term2(xT, p.th, pd_at(p.pd, tN, pdb), s_hxx, s_hxe);
     }
     BDF_SYNC();
     double y[NX];

@@ -18,6 +18,8 @@ constexpr int NU = Model::NU;
 constexpr int NP = Model::NP;
 constexpr int NZ = NX + NU;
 constexpr int NQ = Model::NQ;          // per-problem constants (not learnable)
+constexpr int HAS_TIME = Model::HAS_TIME;   // COCSys_TimeVarying (CPDP.py:394-787): f, c, h depend on the time t explicitly;
+constexpr int NQT = NQ + HAS_TIME;          // the generated model code reads t as one more constant, pd[NQ]
 
 constexpr int FILTER_CAP = 256;        // filter entries per problem (one is added per h-type iteration at most)
 
@@ -69,6 +71,17 @@ struct SolveArgs {
 CPDP_HD const double* theta_of(const SolveArgs& a, int b) { return a.theta + (size_t)b * a.theta_stride; }
 CPDP_HD const double* pdata_of(const SolveArgs& a, int b) { return a.pdata + (size_t)b * NQ; }
 
+// [per-problem constants | t] for a time-varying model; the constants themselves otherwise (no copy)
+struct PdBuf { double v[NQT > 0 ? NQT : 1]; };
+CPDP_HD const double* pd_at(const double* pd, double t, PdBuf& buf) {
+    if (!HAS_TIME) return pd;
+    for (int i = 0; i < NQ; ++i) buf.v[i] = pd[i];
+    buf.v[NQ] = t;
+    return buf.v;
+}
+// node k of numpy.linspace(0, T, N + 1) (CPDP.py:544; the last node is T exactly) -- COCSys' [T / N * k] (CPDP.py:192) has the same bits
+CPDP_HD double grid_time(double T, int N, int k) { return (k == N) ? T : (T / N) * k; }
+
 // One classical RK4 step of (f, c) with frozen control (CPDP.py:117-123).
 CPDP_HD void rk4_step(const double* x, const double* u, const double* th, const double* pd, double DT, double* xn, double& q) {
     double k[NX], xt[NX], c;
@@ -119,7 +132,8 @@ CPDP_D void stage_adjoint_item(const SolveArgs& a, int b, int k) {
     const int idx = b * a.N + k;
     const double DT = a.T / a.N / a.S;
     const double* th = theta_of(a, b);
-    const double* pd = pdata_of(a, b);
+    PdBuf pdb;
+    const double* pd = pd_at(pdata_of(a, b), grid_time(a.T, a.N, k), pdb);      // the time is frozen at t_k over the interval (CPDP.py:512-519,554)
     double x[NX], u[NU];
     {
         const double* xk = a.X + ((size_t)b * (a.N + 1) + k) * NX;
@@ -205,7 +219,7 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
     CPDP_SHARED double s_mu[KPC][NX];
     CPDP_SHARED double s_u[KPC][NU];
     CPDP_SHARED double s_th[KPC][NP];
-    CPDP_SHARED double s_pd[KPC][NQ > 0 ? NQ : 1];
+    CPDP_SHARED double s_pd[KPC][NQT > 0 ? NQT : 1];
     CPDP_SHARED double s_S[KPC][NZ][NX];
     CPDP_SHARED int s_gi[KPC];                 // global interval index b*N+k of each slot, -1 if none
     const int tid = threadIdx.x;
@@ -232,6 +246,9 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
                 else if (e < NU + NP) s_th[q][e - NU] = theta_of(a, b)[e - NU];
                 else s_pd[q][e - NU - NP] = pdata_of(a, b)[e - NU - NP];
             }
+        }
+        if (HAS_TIME) {
+            for (int t = tid; t < KPC; t += HESS_THREADS) if (s_gi[t] >= 0) s_pd[t][NQ] = grid_time(a.T, a.N, s_gi[t] % a.N);
         }
         const bool mine = (kk < KPC) && (s_gi[kk < KPC ? kk : 0] >= 0);
         const int gi = mine ? s_gi[kk] : -1;
@@ -372,7 +389,7 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
     const int N = a.N;
     const double DT = a.T / a.N / a.S;
     const double* th = theta_of(a, b);
-    const double* pd = pdata_of(a, b);
+    const double* pd0 = pdata_of(a, b);
     double* X = a.X + (size_t)b * (N + 1) * NX;
     double* U = a.U + (size_t)b * (N + 1) * NU;
     double* Lam = a.Lam + (size_t)b * (N + 1) * NX;
@@ -395,6 +412,8 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
     // ---- terminal cost derivatives, defect of the initial condition
     if (tid == 0) {
         double h;
+        PdBuf pdb;
+        const double* pd = pd_at(pd0, grid_time(a.T, N, N), pdb);
         Model::term(X + (size_t)N * NX, th, pd, h, s_hx);
         Model::term2(X + (size_t)N * NX, th, pd, s_hxx, s_hxe);
         s_h = h;
@@ -601,6 +620,8 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
         double Jt = 0.0, gt = 0.0;
         for (int k = tid; k <= N; k += nt) {
             double xk[NX];
+            PdBuf pdb;
+            const double* pd = pd_at(pd0, grid_time(a.T, N, k), pdb);
             for (int i = 0; i < NX; ++i) xk[i] = X[(size_t)k * NX + i] + alpha * dX[(size_t)k * NX + i];
             if (k < N) {
                 double uk[NU], xe[NX], q;

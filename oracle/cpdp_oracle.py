@@ -41,7 +41,7 @@ class _Fns:
         self.model = model
         n, m, r = model.n, model.m, model.r
         x, u, th = model.x, model.u, model.theta
-        pd = list(getattr(model, 'pdata', []))
+        pd = list(getattr(model, 'pdata', [])) + ([model.time] if getattr(model, 'time', None) is not None else [])
         z = x + u
         mu = [sp.Symbol('mu%d' % i, real=True) for i in range(n)]
         wc = sp.Symbol('wc', real=True)
@@ -97,31 +97,39 @@ class Oracle:
         self.N, self.S = int(n_grid), int(steps_per_grid)
         self.fn = _Fns(model)
         self.pd = np.zeros(len(getattr(model, 'pdata', [])))   # per-problem constants (e.g. goal position)
+        self.tv = getattr(model, 'time', None) is not None      # COCSys_TimeVarying (CPDP.py:394-787): explicit time in f, c, h
+
+    def _pd(self, t):
+        """model constants for an evaluation at time t: [pdata | t] for a time-varying model"""
+        return np.concatenate((self.pd, [float(t)])) if self.tv else self.pd
 
     # -----------------------------------------------------------------------------------------
     # RK4 interval map (CPDP.py:111-124)
     # -----------------------------------------------------------------------------------------
-    def interval(self, x, u, th, DT):
-        """(x,u) -> (x_end, integral of path cost) over one grid interval: S classical RK4 steps."""
+    def interval(self, x, u, th, DT, tk=0.0):
+        """(x,u) -> (x_end, integral of path cost) over one grid interval: S classical RK4 steps.
+        Time-varying models: every stage of every sub-step is evaluated at the interval's start time tk (CPDP.py:512-519)."""
         X = np.array(x, dtype=float)
         Q = 0.0
         fc = self.fn.fc
+        pd = self._pd(tk)
         for _ in range(self.S):
-            k1, q1 = fc(X, u, th, self.pd)
-            k2, q2 = fc(X + DT / 2 * k1, u, th, self.pd)
-            k3, q3 = fc(X + DT / 2 * k2, u, th, self.pd)
-            k4, q4 = fc(X + DT * k3, u, th, self.pd)
+            k1, q1 = fc(X, u, th, pd)
+            k2, q2 = fc(X + DT / 2 * k1, u, th, pd)
+            k3, q3 = fc(X + DT / 2 * k2, u, th, pd)
+            k4, q4 = fc(X + DT * k3, u, th, pd)
             X = X + DT / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
             Q = Q + DT / 6 * (q1 + 2 * q2 + 2 * q3 + q4)
         return X, Q
 
-    def interval_derivs(self, x, u, th, lam_next, DT):
+    def interval_derivs(self, x, u, th, lam_next, DT, tk=0.0):
         """Value, first derivatives and Hessian of q + lam_next' F for one interval.
 
         First order by forward sensitivities through the 4*S stages, second order by the discrete adjoint:
         Hess = sum_s Sz_s' * Hess_z(mu_s' f + w_s c)(z_s) * Sz_s  with mu_s, w_s the adjoints of stage s."""
         n, m = self.n, self.m
         nz = n + m
+        pd = self._pd(tk)
         E = np.zeros((m, nz)); E[:, n:] = np.eye(m)
         X = np.array(x, dtype=float)
         Sx = np.zeros((n, nz)); Sx[:, :n] = np.eye(n)
@@ -137,7 +145,7 @@ class Oracle:
             for s in range(4):
                 xs = X if s == 0 else X + aco[s] * DT * kprev
                 Ss = Sx if s == 0 else Sx + aco[s] * DT * dkprev
-                f, c, fz, cz = self.fn.stage1(xs, u, th, self.pd)
+                f, c, fz, cz = self.fn.stage1(xs, u, th, pd)
                 Sz = np.vstack([Ss, E])
                 dk = fz @ Sz
                 stages.append((xs, fz, cz.ravel(), Sz))
@@ -162,7 +170,7 @@ class Oracle:
                     kap = kap + aco[s + 1] * DT * kap_next_xi
                 w = bco[s] * DT
                 xs, fz, cz, Sz = stages[s]
-                Hzz, = self.fn.stage2(xs, u, th, self.pd, kap, w)
+                Hzz, = self.fn.stage2(xs, u, th, pd, kap, w)
                 H += Sz.T @ Hzz @ Sz
                 xi = fz[:, :n].T @ kap + w * cz[:n]
                 ax += xi
@@ -173,12 +181,55 @@ class Oracle:
     # -----------------------------------------------------------------------------------------
     # forward solve (CPDP.py:92-198)
     # -----------------------------------------------------------------------------------------
-    def solve(self, x0, horizon, theta, tol=1e-10, max_iter=200, verbose=False, return_info=False):
+    def _riccati_step(self, Ak, Bk, Hk, gLk, dfc, lam, hx, hxx, delta):
+        """Newton step of the equality-constrained NLP through the stage structure of its KKT matrix (block LDL' = Riccati
+        recursion): the linear algebra a banded / structure-exploiting solver (MUMPS inside IPOPT) performs, in O(N n^3)
+        instead of the dense O((N n)^3) factorisation of `solve`'s default path.  Same step as the dense path (checked in
+        tests/test_oracle_kat.py); the inertia is correct iff every Quu block is positive definite.
+        Returns (ok, dX [N+1,n], dU [N,m], lam_new [N+1,n])."""
+        n, m, N = self.n, self.m, self.N
+        V = hxx + delta * np.eye(n)
+        v = hx.copy()
+        Vs, vs, Ks, ks = [None] * (N + 1), [None] * (N + 1), [None] * N, [None] * N
+        Vs[N], vs[N] = V, v
+        for k in range(N - 1, -1, -1):
+            AB = np.hstack([Ak[k], Bk[k]])
+            vt = v + V @ dfc[k + 1]
+            gq = gLk[k] - AB.T @ lam[k + 1]
+            Q = 0.5 * (Hk[k] + Hk[k].T) + delta * np.eye(n + m) + AB.T @ (V @ AB)
+            qv = gq + AB.T @ vt
+            Quu = 0.5 * (Q[n:, n:] + Q[n:, n:].T)
+            try:
+                L = np.linalg.cholesky(Quu)
+            except np.linalg.LinAlgError:
+                return False, None, None, None
+            Qux = 0.5 * (Q[n:, :n] + Q[:n, n:].T)
+            sol = -sla.cho_solve((L, True), np.hstack([Qux, qv[n:, None]]))
+            K, kf = sol[:, :n], sol[:, n]
+            Qxx = 0.5 * (Q[:n, :n] + Q[:n, :n].T)
+            V = Qxx + 0.5 * (Qux.T @ K + K.T @ Qux)
+            v = qv[:n] + Qux.T @ kf
+            Vs[k], vs[k], Ks[k], ks[k] = V, v, K, kf
+        dX = np.zeros((N + 1, n)); dU = np.zeros((N, m)); ln = np.zeros((N + 1, n))
+        dX[0] = dfc[0]
+        for k in range(N):
+            dU[k] = ks[k] + Ks[k] @ dX[k]
+            ln[k] = vs[k] + Vs[k] @ dX[k]
+            dX[k + 1] = dfc[k + 1] + Ak[k] @ dX[k] + Bk[k] @ dU[k]
+        ln[N] = vs[N] + Vs[N] @ dX[N]
+        return True, dX, dU, ln
+
+    def solve(self, x0, horizon, theta, tol=1e-10, max_iter=200, verbose=False, return_info=False, linear_solver='dense'):
+        """linear_solver: 'dense' (default: assembled KKT matrix, LDL' inertia count, dense solve -- the independent check of the
+        kernels' structured recursion) or 'riccati' (stage-structured recursion, used by bench.py's CPU baseline so that the port
+        is not charged for a dense factorisation no sparse NLP solver would perform)."""
         n, m, N = self.n, self.m, self.N
         nz = n + m
         th = np.asarray(theta, dtype=float)
         x0 = np.asarray(x0, dtype=float).ravel()
         DT = horizon / N / self.S
+        # node times: [T/N*k] (CPDP.py:192); numpy.linspace for the time-varying class (CPDP.py:544)
+        tgrid = np.linspace(0, horizon, N + 1) if self.tv else np.array([horizon / N * k for k in range(N + 1)])
         nw = (N + 1) * n + N * m
         ng = (N + 1) * n
         w = np.zeros(nw)          # seed: all zeros (CPDP.py:139,155,167)
@@ -192,10 +243,10 @@ class Oracle:
             g = np.zeros(ng)
             g[:n] = x0 - wv[:n]
             for k in range(N):
-                xe, q = self.interval(wv[ox(k):ox(k) + n], wv[ou(k):ou(k) + m], th, DT)
+                xe, q = self.interval(wv[ox(k):ox(k) + n], wv[ou(k):ou(k) + m], th, DT, tgrid[k])
                 J += q
                 g[(k + 1) * n:(k + 2) * n] = xe - wv[ox(k + 1):ox(k + 1) + n]
-            J += self.fn.term(wv[ox(N):ox(N) + n], th, self.pd)[0]
+            J += self.fn.term(wv[ox(N):ox(N) + n], th, self._pd(tgrid[-1]))[0]
             return J, g
 
         filt = []                 # IPOPT filter: list of (theta, phi) corners
@@ -203,29 +254,41 @@ class Oracle:
         delta_last = 0.0
         info = dict(iters=0, status='max_iter', reg=[], alphas=[])
         for it in range(max_iter + 1):
+            structured = (linear_solver == 'riccati')
             gradJ = np.zeros(nw)
-            W = np.zeros((nw, nw))
-            Ag = np.zeros((ng, nw))
+            W = None if structured else np.zeros((nw, nw))
+            Ag = None if structured else np.zeros((ng, nw))
             g = np.zeros(ng)
             J = 0.0
             g[:n] = x0 - w[:n]
-            Ag[:n, :n] = -np.eye(n)
+            if not structured:
+                Ag[:n, :n] = -np.eye(n)
+            Aks, Bks, Hks, gLs = [], [], [], []
+            gradL = np.zeros(nw)                       # gradient of the Lagrangian, assembled stage-wise
+            gradL[:n] -= lam[:n]
             for k in range(N):
                 xk, uk = w[ox(k):ox(k) + n], w[ou(k):ou(k) + m]
                 lk1 = lam[(k + 1) * n:(k + 2) * n]
-                xe, q, A, B, dQ, _, H = self.interval_derivs(xk, uk, th, lk1, DT)
+                xe, q, A, B, dQ, gLk, H = self.interval_derivs(xk, uk, th, lk1, DT, tgrid[k])
                 J += q
                 g[(k + 1) * n:(k + 2) * n] = xe - w[ox(k + 1):ox(k + 1) + n]
                 gradJ[ox(k):ox(k) + nz] += dQ
-                W[ox(k):ox(k) + nz, ox(k):ox(k) + nz] += H
-                Ag[(k + 1) * n:(k + 2) * n, ox(k):ox(k) + n] = A
-                Ag[(k + 1) * n:(k + 2) * n, ou(k):ou(k) + m] = B
-                Ag[(k + 1) * n:(k + 2) * n, ox(k + 1):ox(k + 1) + n] = -np.eye(n)
-            hv, hx, hxx, _ = self.fn.term(w[ox(N):ox(N) + n], th, self.pd)
+                gradL[ox(k):ox(k) + nz] += gLk
+                gradL[ox(k + 1):ox(k + 1) + n] -= lk1
+                if structured:
+                    Aks.append(A); Bks.append(B); Hks.append(H); gLs.append(gLk)
+                else:
+                    W[ox(k):ox(k) + nz, ox(k):ox(k) + nz] += H
+                    Ag[(k + 1) * n:(k + 2) * n, ox(k):ox(k) + n] = A
+                    Ag[(k + 1) * n:(k + 2) * n, ou(k):ou(k) + m] = B
+                    Ag[(k + 1) * n:(k + 2) * n, ox(k + 1):ox(k + 1) + n] = -np.eye(n)
+            hv, hx, hxx, _ = self.fn.term(w[ox(N):ox(N) + n], th, self._pd(tgrid[-1]))
             J += hv
             gradJ[ox(N):ox(N) + n] += hx.ravel()
-            W[ox(N):ox(N) + n, ox(N):ox(N) + n] += hxx
-            kkt_err = max(np.abs(gradJ + Ag.T @ lam).max(), np.abs(g).max())
+            gradL[ox(N):ox(N) + n] += hx.ravel()
+            if not structured:
+                W[ox(N):ox(N) + n, ox(N):ox(N) + n] += hxx
+            kkt_err = max(np.abs(gradL).max() if structured else np.abs(gradJ + Ag.T @ lam).max(), np.abs(g).max())
             if verbose:
                 print('it %3d  J=%.10f  |gradL|=%.3e |g|=%.3e' % (it, J, np.abs(gradJ + Ag.T @ lam).max(), np.abs(g).max()))
             if kkt_err < tol:
@@ -237,12 +300,18 @@ class Oracle:
             delta = 0.0
             first = True
             while True:
-                K = np.zeros((nw + ng, nw + ng))
-                K[:nw, :nw] = W + delta * np.eye(nw)
-                K[:nw, nw:] = Ag.T
-                K[nw:, :nw] = Ag
-                if _inertia_ok(K, nw, ng):
-                    break
+                if structured:
+                    ok_, dXs, dUs, lns = self._riccati_step(Aks, Bks, Hks, gLs, g.reshape(N + 1, n), lam.reshape(N + 1, n),
+                                                            hx.ravel(), hxx, delta)
+                    if ok_:
+                        break
+                else:
+                    K = np.zeros((nw + ng, nw + ng))
+                    K[:nw, :nw] = W + delta * np.eye(nw)
+                    K[:nw, nw:] = Ag.T
+                    K[nw:, :nw] = Ag
+                    if _inertia_ok(K, nw, ng):
+                        break
                 if first:
                     delta = 1e-4 if delta_last == 0.0 else max(1e-20, delta_last / 3.0)
                     first = False
@@ -253,8 +322,12 @@ class Oracle:
             if delta > 0:
                 delta_last = delta
             info['reg'].append(delta)
-            sol = np.linalg.solve(K, -np.concatenate([gradJ, g]))
-            d, lam_new = sol[:nw], sol[nw:]
+            if structured:
+                d = np.concatenate([np.hstack([dXs[:N], dUs]).ravel(), dXs[N]])
+                lam_new = lns.ravel()
+            else:
+                sol = np.linalg.solve(K, -np.concatenate([gradJ, g]))
+                d, lam_new = sol[:nw], sol[nw:]
             # ---- IPOPT filter line search (Waechter & Biegler 2006, Sec. 2.3; no barrier term: phi = J,
             #      theta = |g|_1; constants = IPOPT defaults gamma_theta 1e-5, gamma_phi 1e-8, delta 1, s_theta 1.1,
             #      s_phi 2.3, eta_phi 1e-8, theta_min/max = 1e-4/1e4 * max(1, theta(x0)); no second-order correction
@@ -305,7 +378,7 @@ class Oracle:
         X = sc[:, :n].copy()
         U = sc[:, n:].copy()
         U[-1, :] = U[-2, :]
-        time_grid = np.array([horizon / N * k for k in range(N + 1)])
+        time_grid = tgrid
         Lam = lam.reshape(-1, n).copy()
         if return_info:
             return time_grid, X, U, Lam, info
@@ -314,14 +387,14 @@ class Oracle:
     # -----------------------------------------------------------------------------------------
     # auxiliary system (CPDP.py:253-381)
     # -----------------------------------------------------------------------------------------
-    def _coeffs(self, x, u, lam, th):
-        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue = self.fn.pmp(x, u, lam, th, self.pd)
+    def _coeffs(self, x, u, lam, th, t=0.0):
+        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue = self.fn.pmp(x, u, lam, th, self._pd(t))
         invHuu = np.linalg.inv(Huu)
         return fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu
 
-    def riccati_rhs(self, x, u, lam, th, P, W, reassoc=False):
-        """CPDP.py:262-274"""
-        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu = self._coeffs(x, u, lam, th)
+    def riccati_rhs(self, x, u, lam, th, P, W, reassoc=False, t=0.0):
+        """CPDP.py:262-274 (time-varying: :650-667)"""
+        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu = self._coeffs(x, u, lam, th, t)
         G = fu @ invHuu
         HxuinvHuu = Hxu @ invHuu
         A = fx - G @ Hxu.T
@@ -337,11 +410,11 @@ class Oracle:
         W_dot = P @ R @ W - A.T @ W - P @ r - q
         return P_dot, W_dot
 
-    def riccati_jac(self, x, u, lam, th, P, W):
+    def riccati_jac(self, x, u, lam, th, P, W, t=0.0):
         """Closed-form Jacobian of ``riccati_rhs`` w.r.t. the row-major state [vec P | vec W] (the matrix scipy's BDF
         approximates by finite differences when the reference calls it without ``jac``, CPDP.py:335):
         d(Pdot)[dP] = -((A'-PR) dP + dP (A-RP)),  d(Wdot)[dP, dW] = dP (RW - r_) + (PR - A') dW."""
-        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu = self._coeffs(x, u, lam, th)
+        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu = self._coeffs(x, u, lam, th, t)
         n, r = P.shape[0], W.shape[1]
         G = fu @ invHuu
         A = fx - G @ Hxu.T
@@ -354,14 +427,14 @@ class Oracle:
         J[n * n:, n * n:] = np.kron(P @ R - A.T, np.eye(r))
         return J
 
-    def aux_controller(self, x, u, lam, th, P, W, Xa):
+    def aux_controller(self, x, u, lam, th, P, W, Xa, t=0.0):
         """CPDP.py:294-295"""
-        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu = self._coeffs(x, u, lam, th)
+        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu = self._coeffs(x, u, lam, th, t)
         return -invHuu @ ((Hxu.T + fu.T @ P) @ Xa + fu.T @ W + Hue)
 
-    def aux_rhs(self, x, u, lam, th, P, W, Xa):
+    def aux_rhs(self, x, u, lam, th, P, W, Xa, t=0.0):
         """CPDP.py:295-297"""
-        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu = self._coeffs(x, u, lam, th)
+        fx, fu, fe, Hxx, Hxu, Hxe, Huu, Hue, invHuu = self._coeffs(x, u, lam, th, t)
         Ua = -invHuu @ ((Hxu.T + fu.T @ P) @ Xa + fu.T @ W + Hue)
         return fx @ Xa + fu @ Ua + fe
 
@@ -372,7 +445,8 @@ class Oracle:
         finite-difference one (same solver, same control logic); ``reassoc=True`` evaluates the Riccati right-hand
         side with a different association of the same matrix products (measures how far roundoff alone moves the
         as-shipped result through the finite-difference Jacobian)."""
-        back = dict({'method': 'BDF'} if back is None else back)
+        # as shipped: BDF for COCSys (CPDP.py:335), solve_ivp's default RK45 for COCSys_TimeVarying (CPDP.py:740)
+        back = dict(({} if self.tv else {'method': 'BDF'}) if back is None else back)
         reassoc = back.pop('reassoc', False)
         fwd = {} if fwd is None else fwd
         n, m, r, N = self.n, self.m, self.r, self.N
@@ -389,17 +463,17 @@ class Oracle:
             P = vec_PW[:n * n].reshape(n, n)
             W = vec_PW[n * n:].reshape(n, -1)
             x, u, lam = split(t)
-            Pd, Wd = self.riccati_rhs(x, u, lam, th, P, W, reassoc=reassoc)
+            Pd, Wd = self.riccati_rhs(x, u, lam, th, P, W, reassoc=reassoc, t=t)
             return np.concatenate((Pd.flatten(), Wd.flatten()))
 
         if back.get('jac') == 'closed':
             def vec_PW_jac(t, vec_PW):
                 x, u, lam = split(t)
-                return self.riccati_jac(x, u, lam, th, vec_PW[:n * n].reshape(n, n), vec_PW[n * n:].reshape(n, -1))
+                return self.riccati_jac(x, u, lam, th, vec_PW[:n * n].reshape(n, n), vec_PW[n * n:].reshape(n, -1), t=t)
             back['jac'] = vec_PW_jac
 
         xT = opt_sol(float(time_grid[-1]))[:n]
-        _, _, hxx, hxe = self.fn.term(xT, th, self.pd)
+        _, _, hxx, hxe = self.fn.term(xT, th, self._pd(time_grid[-1]))
         PW = np.zeros((N + 1, n * n + n * r))
         PW[-1, :] = np.concatenate((hxx.flatten(), hxe.flatten()))
         for k in range(N, 0, -1):
@@ -419,13 +493,13 @@ class Oracle:
             Xa = vecX.reshape(n, r)
             x, u, lam = split(t)
             P, W = PWat(t)
-            return self.aux_rhs(x, u, lam, th, P, W, Xa).flatten()
+            return self.aux_rhs(x, u, lam, th, P, W, Xa, t=t).flatten()
 
         Xa = np.zeros((N + 1, n * r))
         Ua = np.zeros((N + 1, m * r))
         x, u, lam = split(0)
         P, W = PWat(0)
-        Ua[0, :] = self.aux_controller(x, u, lam, th, P, W, Xa[0].reshape(n, r)).flatten()
+        Ua[0, :] = self.aux_controller(x, u, lam, th, P, W, Xa[0].reshape(n, r), t=0.0).flatten()
         for k in range(N):
             t_span = [time_grid[k], time_grid[k + 1]]
             sol = solve_ivp(vec_aux_ode, t_span, Xa[k, :], t_eval=[time_grid[k + 1]], **fwd)
@@ -434,7 +508,7 @@ class Oracle:
             Xa[k + 1, :] = sol.y.flatten()
             x, u, lam = split(float(time_grid[k + 1]))
             P, W = PWat(float(time_grid[k + 1]))
-            Ua[k + 1, :] = self.aux_controller(x, u, lam, th, P, W, Xa[k + 1].reshape(n, r)).flatten()
+            Ua[k + 1, :] = self.aux_controller(x, u, lam, th, P, W, Xa[k + 1].reshape(n, r), t=time_grid[k + 1]).flatten()
         if return_counts:
             return Xa, Ua, PW, counts
         return Xa, Ua, PW
@@ -459,9 +533,9 @@ class Oracle:
         return loss, dl
 
     # -----------------------------------------------------------------------------------------
-    def grad_iter(self, x0, horizon, theta, taus, waypoints, back=None, fwd=None, tol=1e-10):
+    def grad_iter(self, x0, horizon, theta, taus, waypoints, back=None, fwd=None, tol=1e-10, linear_solver='dense'):
         """One CPDP gradient iteration for one OCP: (loss, dL/dtheta, extras)."""
-        tg, X, U, Lam, info = self.solve(x0, horizon, theta, tol=tol, return_info=True)
+        tg, X, U, Lam, info = self.solve(x0, horizon, theta, tol=tol, return_info=True, linear_solver=linear_solver)
         Xa, Ua, PW = self.aux(tg, X, U, Lam, theta, back=back, fwd=fwd)
         loss, dl = self.loss_grad(taus, waypoints, tg, X, Xa)
         return loss, dl, dict(time_grid=tg, X=X, U=U, Lam=Lam, Xa=Xa, Ua=Ua, PW=PW, info=info)

@@ -33,6 +33,7 @@ class OracleModel:
         self.final = sp.sympify(final)
         self.sel = list(sel)
         self.pdata = list(pdata)      # per-problem constants (not learnable), e.g. a symbolic goal position
+        self.time = None              # explicit time symbol of a COCSys_TimeVarying model (CPDP.py:434)
 
 
 def _syms(names):
@@ -71,7 +72,27 @@ def pendulum(l=1.0, m=1.0, damping=0.1, wu=0.01):
     return OracleModel('pendulum', [q, dq], [u], [beta, wq, wdq], beta * f, beta * c, h, sel=[0])
 
 
-def robotarm(l1=1.0, m1=1.0, l2=1.0, m2=1.0, g=0.0, wu=0.5):
+def pendulum_timewarp(order=2, l=1.0, m=1.0, damping=0.1, wu=0.01):
+    """/root/reference/Examples/pendulum_timewarping.py:15-56: the pendulum under COCSys_TimeVarying with the polynomial
+    time-warping speed v(t) = beta1 + 2 beta2 t + 3 beta3 t^2 + ... (order 1 is the script's active variant, 2-4 its
+    commented ones); dyn = v f, path = v c, final = h."""
+    q, dq = _syms('q dq')
+    u, = _syms('u')
+    t, = _syms('t')
+    betas = _syms(' '.join('beta%d' % (i + 1) for i in range(order)))
+    wq, wdq = _syms('wq wdq')
+    g = 10
+    inertia = sp.Rational(1, 3) * m * l * l
+    f = sp.Matrix([dq, (u - m * g * l * sp.sin(q) - damping * dq) / inertia])
+    h = wq * (q - math.pi) ** 2 + wdq * dq ** 2
+    c = h + wu * u ** 2
+    v = sum((i + 1) * betas[i] * t ** i for i in range(order))
+    mdl = OracleModel('pendulum_tw%d' % order, [q, dq], [u], list(betas) + [wq, wdq], v * f, v * c, h, sel=[0])
+    mdl.time = t
+    return mdl
+
+
+def robotarm(l1=1.0, m1=1.0, l2=1.0, m2=1.0, g=0.0, wu=0.5, cost='polynomial'):
     q1, q2, dq1, dq2 = _syms('q1 q2 dq1 dq2')
     u1, u2 = _syms('u1 u2')
     beta, w1s, w1, w2s, w2 = _syms('beta w_q1_sq w_q1 w_q2_sq w_q2')
@@ -89,6 +110,12 @@ def robotarm(l1=1.0, m1=1.0, l2=1.0, m2=1.0, g=0.0, wu=0.5):
     Minv = sp.Matrix([[M22, -M12], [-M12, M11]]) / det
     ddq = Minv * (-C - G + sp.Matrix([u1, u2]))
     f = sp.Matrix([dq1, dq2, ddq[0], ddq[1]])
+    if cost == 'weighted_distance':      # JinEnv.py:239-285 (initCost_WeightedDistance), goal [pi/2, 0, 0, 0]
+        wq1, wq2, wdq1, wdq2 = _syms('wq1 wq2 wdq1 wdq2')
+        h = wq1 * (q1 - math.pi / 2) ** 2 + wq2 * (q2 - 0) ** 2 + wdq1 * (dq1 - 0) ** 2 + wdq2 * (dq2 - 0) ** 2
+        c = h + wu * (u1 * u1 + u2 * u2)
+        return OracleModel('robotarm_wd', [q1, q2, dq1, dq2], [u1, u2], [beta, wq1, wq2, wdq1, wdq2],
+                           beta * f, beta * c, h, sel=[0, 1])
     c = w1 * q1 + w1s * q1 * q1 / 2 + w2 * q2 + w2s * q2 * q2 / 2 + wu * (u1 ** 2 + u2 ** 2)
     h = 100 * ((q1 - math.pi / 2) ** 2 + q2 ** 2 + dq1 ** 2 + dq2 ** 2)
     return OracleModel('robotarm', [q1, q2, dq1, dq2], [u1, u2], [beta, w1s, w1, w2s, w2],
@@ -96,7 +123,7 @@ def robotarm(l1=1.0, m1=1.0, l2=1.0, m2=1.0, g=0.0, wu=0.5):
 
 
 def quadrotor(goal_r=None, goal_v=(0., 0., 0.), goal_q=(1., 0., 0., 0.), goal_w=(0., 0., 0.),
-              J=(1.0, 1.0, 1.0), mass=1.0, l=1.0, c=0.02, w_thrust=0.1):
+              J=(1.0, 1.0, 1.0), mass=1.0, l=1.0, c=0.02, w_thrust=0.1, cost='polynomial'):
     r = _syms('rx ry rz'); v = _syms('vx vy vz'); q = _syms('q0 q1 q2 q3'); w = _syms('wx wy wz')
     f_ = _syms('f1 f2 f3 f4')
     beta, wxs, wx_, wys, wy_, wzs, wz_ = _syms('beta w_xsq w_x w_ysq w_y w_zsq w_z')
@@ -112,13 +139,26 @@ def quadrotor(goal_r=None, goal_v=(0., 0., 0.), goal_q=(1., 0., 0., 0.), goal_w=
     path = (wxs * r[0] ** 2 / 2 + wx_ * r[0] + wys * r[1] ** 2 / 2 + wy_ * r[1] + wzs * r[2] ** 2 / 2 + wz_ * r[2]
             + w_thrust * sum(fi ** 2 for fi in f_))
     att = (sp.eye(3) - _dcm(goal_q).T * _dcm(q)).trace()
+    thr = sum(fi ** 2 for fi in f_)
+    if cost == 'weighted':               # JinEnv.py:755-815 (initCost): scalar weights [wr, wv, wq, ww]
+        wr, wv, wq, ww = _syms('wr wv wq ww')
+        h = (wr * sum((a - b) ** 2 for a, b in zip(r, goal_r)) + wv * sum((a - b) ** 2 for a, b in zip(v, goal_v))
+             + ww * sum((a - b) ** 2 for a, b in zip(w, goal_w)) + wq * att)
+        return OracleModel('quadrotor_cost1', r + v + q + w, f_, [beta, wr, wv, wq, ww], beta * f, beta * (h + w_thrust * thr), h,
+                           sel=[0, 1, 2], pdata=pdata)
+    if cost == 'per_axis':               # JinEnv.py:817-884 (initCost2): [wrx wry wrz wvx wvy wvz wwx wwy wwz wq]
+        ws = _syms('wrx wry wrz wvx wvy wvz wwx wwy wwz wq')
+        h = (sum(ws[i] * (r[i] - goal_r[i]) ** 2 for i in range(3)) + sum(ws[3 + i] * (v[i] - goal_v[i]) ** 2 for i in range(3))
+             + sum(ws[6 + i] * (w[i] - goal_w[i]) ** 2 for i in range(3)) + ws[9] * att)
+        return OracleModel('quadrotor_cost2', r + v + q + w, f_, [beta] + ws, beta * f, beta * (h + w_thrust * thr), h,
+                           sel=[0, 1, 2], pdata=pdata)
     h = (1 * sum((a - b) ** 2 for a, b in zip(r, goal_r)) + 11 * sum((a - b) ** 2 for a, b in zip(v, goal_v))
          + 100 * att + 10 * sum((a - b) ** 2 for a, b in zip(w, goal_w)))
     return OracleModel('quadrotor', r + v + q + w, f_, [beta, wxs, wx_, wys, wy_, wzs, wz_],
                        beta * f, beta * path, h, sel=[0, 1, 2], pdata=pdata)
 
 
-def rocket(J=(1.0, 1.0, 1.0), mass=1.0, l=1.0, wthrust=0.1):
+def rocket(J=(1.0, 1.0, 1.0), mass=1.0, l=1.0, wthrust=0.1, cost='cost2'):
     r = _syms('rx ry rz'); v = _syms('vx vy vz'); q = _syms('q0 q1 q2 q3'); w = _syms('wx wy wz')
     u = _syms('ux uy uz')
     names = 'wrx wry wrz wvx wvy wvz wwx wwy wwz wsidethrust wtilt'
@@ -132,6 +172,18 @@ def rocket(J=(1.0, 1.0, 1.0), mass=1.0, l=1.0, wthrust=0.1):
     f = sp.Matrix([*v, *dv, *_quat_rate(q, w), *_euler(J, r_T.cross(T_B), w)])
     bx = C_I_B * sp.Matrix([1, 0, 0])
     tilt = bx[1] ** 2 + bx[2] ** 2
+    side, thr = u[1] ** 2 + u[2] ** 2, sum(ui ** 2 for ui in u)
+    if cost == 'scalar':                 # JinEnv.py:1328-1399 (initCost): [wr, wv, wtilt, wsidethrust, ww]; side thrust in the path cost only
+        swr, swv, swtilt, swside, sww = _syms('wr wv wtilt wsidethrust ww')
+        hs = (swr * sum(a ** 2 for a in r) + swv * sum(a ** 2 for a in v) + sww * sum(a ** 2 for a in w) + swtilt * tilt)
+        return OracleModel('rocket_cost1', r + v + q + w, u, [beta, swr, swv, swtilt, swside, sww], beta * f,
+                           beta * (hs + swside * side + wthrust * thr), hs, sel=[0, 1, 2, 6, 7, 8, 9])
+    if cost == 'ex':                     # JinEnv.py:1475-1551 (initCost_Ex): per-axis weights, tilt BEFORE side thrust in theta,
+        ex = _syms('wrx wry wrz wvx wvy wvz wwx wwy wwz wtilt wsidethrust')      # and the side-thrust term also in the final cost
+        hx = (sum(a * b ** 2 for a, b in zip(ex[0:3], r)) + sum(a * b ** 2 for a, b in zip(ex[3:6], v))
+              + sum(a * b ** 2 for a, b in zip(ex[6:9], w)) + ex[9] * tilt + ex[10] * side)
+        return OracleModel('rocket_costex', r + v + q + w, u, [beta] + ex, beta * f, beta * (hx + wthrust * thr), hx,
+                           sel=[0, 1, 2, 6, 7, 8, 9])
     h = (sum(a * b ** 2 for a, b in zip(wr, r)) + sum(a * b ** 2 for a, b in zip(wv, v))
          + sum(a * b ** 2 for a, b in zip(ww, w)) + wtilt * tilt)
     c = h + wside * (u[1] ** 2 + u[2] ** 2) + wthrust * sum(ui ** 2 for ui in u)

@@ -33,9 +33,9 @@ class NumpyMem:
 
 def emu_oc(name, tsan=False, **kw):
     """COCSys for standard model `name` bound to the host-emulated kernels."""
-    oc = standard.STANDARD[name](**kw)
+    oc = (standard.STANDARD.get(name) or standard.VARIANTS[name])(**kw)
     text, info = codegen.generate_model_header(name, oc.state, oc.control, oc.auxvar, oc.dyn, oc.path_cost,
-                                               oc.final_cost, oc.pvar)
+                                               oc.final_cost, oc.pvar, time=getattr(oc, 'time', None))
     os.makedirs(_BUILD, exist_ok=True)
     src = ""
     for fn in sorted(os.listdir(_capi.CSRC)):

@@ -29,13 +29,16 @@ def run_problem(args):
     kind, n_grid, x0, T, theta, pd, taus, wp = args
     mdl = getattr(models, kind)()
     orc = Oracle(mdl, n_grid=n_grid)
+    variants = (('asshipped', {'method': 'BDF'}, {}), ('rk45', {}, {}), ('tight', TIGHT, TIGHT),
+                ('asshipped_cj', {'method': 'BDF', 'jac': 'closed'}, {}),
+                ('asshipped_ra', {'method': 'BDF', 'reassoc': True}, {}))
+    if orc.tv:      # COCSys_TimeVarying integrates both sweeps with solve_ivp's default RK45 (CPDP.py:740,773)
+        variants = (('asshipped', {}, {}), ('rk45', {}, {}), ('tight', TIGHT, TIGHT))
     if pd is not None:
         orc.pd = np.asarray(pd, dtype=float)
     tg, X, U, Lam, info = orc.solve(x0, T, theta, return_info=True)
     out = dict(X=X, U=U, Lam=Lam, iters=info['iters'], J=info['J'], kkt=info['kkt'])
-    for tag, back, fwd in (('asshipped', {'method': 'BDF'}, {}), ('rk45', {}, {}), ('tight', TIGHT, TIGHT),
-                           ('asshipped_cj', {'method': 'BDF', 'jac': 'closed'}, {}),
-                           ('asshipped_ra', {'method': 'BDF', 'reassoc': True}, {})):
+    for tag, back, fwd in variants:
         try:
             Xa, Ua, PW, cnt = orc.aux(tg, X, U, Lam, theta, back=back, fwd=fwd, return_counts=True)
         except OracleIntegrationError as e:      # solve_ivp gave up (the reference would crash here): record it
@@ -79,10 +82,22 @@ def main():
         tg, Xs, _, _ = orc.solve(rb['x0'][b], 3.0, rb['theta_true'])
         rjobs.append(('rocket', 15, rb['x0'][b], 3.0, rb['theta0'], None, tg[rb['tau_idx']], Xs[rb['tau_idx']][:, rb['sel']]))
     jobs['rocket'] = rjobs
+    # Examples/pendulum_timewarping.py:60-68 (T = 0.2, five waypoints) with the second-order time-warping polynomial
+    tw_T = 0.2
+    tw_taus = np.array([0.1, 0.3, 0.6, 0.7, 0.9]) / 1 * tw_T
+    tw_wp = np.array([[0.5], [1.8], [2.0], [2.9], [3.1]])
+    jobs['pendulum_tw2'] = [('pendulum_timewarp', 10, np.zeros(2), tw_T, np.array(th), None, tw_taus, tw_wp)
+                            for th in ([1.0, 1.0, 1.0, 1.0], [2.5, 0.7, 0.8, 1.3], [4.0, -1.5, 1.2, 0.6])]
     qb = synthetic.quad_batch(4096)
     jobs['quad50'] = [('quadrotor', 50, qb['x0'][b], 1.0, qb['theta'], qb['goal'][b], qb['taus'], qb['wp'][b]) for b in range(6)]
     g = np.load(os.path.join(HERE, 'quad_run.npz'))
     jobs['quadkat'] = [('quadrotor', 25, g['ini_state'], 1.0, g['parameter_trace'][0], g['goal_position'], g['time_grid'], g['waypoints'])]
+    # BASELINE configs[3]: Examples/quad_example.py:31-57 as scripted (start [0,0,.6], goal [3,3,1.5], five waypoints at
+    # tau = [1..5]/6 after the learner's normalisation, lib/QuadAlgorithm.py:221-223; n_grid 25; theta0 of :235)
+    jobs['quadexample'] = [('quadrotor', 25, np.array([0, 0, 0.6, 0, 0, 0, 1.0, 0, 0, 0, 0, 0, 0]), 1.0,
+                            np.array([1, 0.1, 0.1, 0.1, 0.1, 0.1, -1.0]), np.array([3.0, 3.0, 1.5]),
+                            np.array([1.0, 2.0, 3.0, 4.0, 5.0]) / 6,
+                            np.array([[0.5, 0.5, 0.6], [1.0, 1.0, 0.8], [1.5, 1.5, 1.0], [2.0, 2.0, 1.2], [2.5, 2.5, 1.5]]))]
     only = [a for a in sys.argv[1:] if not a.startswith('-')]
     if only:
         jobs = {k: v for k, v in jobs.items() if k in only}

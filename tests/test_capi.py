@@ -18,7 +18,9 @@ def _declared_symbols():
 
 @pytest.mark.parametrize("model,dims", [("pendulum", (2, 1, 3, 0)), ("robotarm", (4, 2, 5, 0)),
                                         ("rocket", (13, 3, 12, 0)), ("quadrotor", (13, 4, 7, 3)),
-                                        ("cartpole", (4, 1, 5, 0))])
+                                        ("cartpole", (4, 1, 5, 0)), ("pendulum_tw2", (2, 1, 4, 0)),
+                                        ("robotarm_wd", (4, 2, 5, 0)), ("quadrotor_cost1", (13, 4, 5, 3)),
+                                        ("quadrotor_cost2", (13, 4, 11, 3)), ("rocket_cost1", (13, 3, 6, 0))])
 def test_library_exports(model, dims):
     so = os.path.join(_capi.LIB_DIR, "libcpdp_%s.so" % model)
     if not os.path.exists(so):
@@ -27,6 +29,7 @@ def test_library_exports(model, dims):
     raw = ctypes.CDLL(so)
     syms = _declared_symbols()
     assert "cpdp_solve" in syms and "cpdp_aux" in syms and "cpdp_reduce" in syms
+    assert "cpdp_pack_rows" in syms and "cpdp_reduce_rows" in syms and "cpdp_optim_step" in syms
     for s in syms:
         assert hasattr(raw, s), "missing export %s" % s
     assert (lib.n, lib.m, lib.r, lib.q) == dims

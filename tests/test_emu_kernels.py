@@ -161,6 +161,30 @@ def test_quad_k4_gradient_bdf_vs_stored_run(quad):
     assert _rel(aux["dtheta"][0], (P[0] - P[1]) / lr) < 1e-5
 
 
+def test_pendulum_timewarping_vs_oracle():
+    """COCSys_TimeVarying (reference CPDP.py:394-787, Examples/pendulum_timewarping.py with v(t) = beta1 + 2 beta2 t):
+    frozen-time RK4 map + linspace grid in the solve, RK45 for both sweeps, the time reaching every model function."""
+    oc = emu_oc("pendulum_tw2")
+    assert type(oc).__name__ == "COCSys_TimeVarying" and oc.aux_mode == oc.MODE_RK45
+    orc = Oracle(models.pendulum_timewarp(2), n_grid=10)
+    th, T = np.array([2.5, 0.7, 0.8, 1.3]), 0.2
+    tg, opt_sol = oc.cocSolver([0.0, 0.0], T, th)
+    tgo, X, U, Lam, info = orc.solve([0.0, 0.0], T, th, return_info=True)
+    assert oc.last_status == 1 and oc.last_iters == info["iters"]
+    assert np.array_equal(tg, tgo) and np.array_equal(tg, np.linspace(0, T, 11))
+    nodes = opt_sol(tg)
+    assert np.abs(nodes[:, :2] - X).max() < 1e-10 and np.abs(nodes[:, 2:3] - U).max() < 1e-9 and np.abs(nodes[:, 3:] - Lam).max() < 1e-9
+    aux_sol = oc.auxSysSolver(tg, opt_sol, th)
+    Xa, Ua, PW, cnt = orc.aux(tgo, X, U, Lam, th, return_counts=True)          # default for the class: RK45 / RK45
+    got = aux_sol(tg)
+    assert oc.last_aux_status == 0
+    assert (oc.last_aux_counters[0], oc.last_aux_counters[2]) == (cnt["back_rhs"], cnt["fwd_rhs"])
+    assert _rel(got[:, :8], Xa) < 1e-9 and _rel(got[:, 8:], Ua) < 1e-9
+    # the time really enters: beta2 moves the solution
+    tg2, sol2 = oc.cocSolver([0.0, 0.0], T, np.array([2.5, 0.0, 0.8, 1.3]))
+    assert np.abs(sol2(tg2) - nodes).max() > 1e-3
+
+
 def test_cartpole_through_codegen_vs_oracle():
     """a JinEnv definition no example script uses (CartPole) goes through the same code generation and
     kernels; checked against the oracle's independent restatement of the model."""

@@ -109,6 +109,43 @@ def test_pendulum(torch_mod):
     _check_case(oc, _fx("pendulum"), [0], _modes(oc))
 
 
+def test_pendulum_timewarping(torch_mod):
+    """COCSys_TimeVarying (CPDP.py:394-787) on Examples/pendulum_timewarping.py with the second-order warping polynomial
+    v(t) = beta1 + 2 beta2 t: frozen-time RK4 map, linspace grid, RK45 for both sweeps (the class' as-shipped integrators)."""
+    oc = _oc("pendulum_tw2", 10)
+    assert oc.aux_mode == oc.MODE_RK45 and type(oc).__name__ == "COCSys_TimeVarying"
+    fx = _fx("pendulum_tw2")
+    modes = [("asshipped", oc.MODE_RK45, 1e-3, 1e-6, 1e-3, 1e-6), ("tight", oc.MODE_RK45, 1e-10, 1e-12, 1e-10, 1e-12)]
+    sol = oc.cocSolverBatch(fx["x0"], float(fx["T"]), fx["theta"])
+    assert np.array_equal(sol["time_grid"], np.linspace(0, float(fx["T"]), 11))
+    assert np.array_equal(_np(sol["iters"]), fx["iters"]) and (_np(sol["status"]) == 1).all()
+    for key in ("X", "U", "Lam"):
+        assert _rel(_np(sol[key]), fx[key]) < TRAJ_RTOL, key
+    for tag, mode, rb, ab, rf, af in modes:
+        oc.aux_mode = mode
+        oc.rtol_back, oc.atol_back, oc.rtol_fwd, oc.atol_fwd = rb, ab, rf, af
+        aux = oc.auxSysSolverBatch(sol, fx["taus"], fx["wp"], [0])
+        assert (_np(aux["aux_status"]) == 0).all()
+        cnt = _np(aux["counters"])
+        assert np.array_equal(cnt[:, [0, 2]], fx["cnt_" + tag]), (tag, cnt, fx["cnt_" + tag])     # same step sequences as scipy
+        for b in range(fx["x0"].shape[0]):
+            assert abs(_np(aux["loss"])[b] - fx["loss_" + tag][b]) <= 1e-8 * max(1.0, abs(fx["loss_" + tag][b]))
+            assert _rel(_np(aux["dtheta"])[b], fx["dl_" + tag][b]) < GRAD_RTOL, (tag, b)
+            assert _rel(_np(aux["Xa"])[b], fx["Xa_" + tag][b]) < GRAD_RTOL and _rel(_np(aux["Ua"])[b], fx["Ua_" + tag][b]) < 10 * GRAD_RTOL
+    # the reference-shaped single-problem API and three steps of the script's learning loop (:83-90)
+    th = fx["theta"][0].copy()
+    oc.aux_mode = oc.MODE_RK45
+    oc.rtol_back, oc.atol_back, oc.rtol_fwd, oc.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
+    time_grid, opt_sol = oc.cocSolver([0.0, 0.0], float(fx["T"]), th)
+    auxsys_sol = oc.auxSysSolver(time_grid, opt_sol, th)
+    loss, diff = 0.0, np.zeros(4)
+    for k, t in enumerate(fx["taus"][0]):
+        measure = opt_sol(t)[0:1]
+        loss += np.linalg.norm(fx["wp"][0][k] - measure) ** 2
+        diff += np.matmul(measure - fx["wp"][0][k], auxsys_sol(t)[0:8].reshape((2, 4))[0:1, :])
+    assert abs(loss - fx["loss_asshipped"][0]) < 1e-8 * loss and _rel(diff, fx["dl_asshipped"][0]) < GRAD_RTOL
+
+
 def test_robotarm(torch_mod):
     oc = _oc("robotarm", 30)
     _check_case(oc, _fx("robotarm"), [0, 1], _modes(oc))
@@ -437,3 +474,33 @@ def test_bdf_counters_equal_scipy(torch_mod):
             got = [int(cnt[b][0]), int(cnt[b][1]), int(cnt[b][4]), int(cnt[b][5])]
             assert got == [int(v) for v in want[b]], (case, b, got, want[b].tolist())
             assert int(cnt[b][2]) == int(fx["cnt_asshipped_cj"][b][1]), (case, b)      # forward RK45 rhs evaluations
+
+
+def test_quad_example_script_config(torch_mod):
+    """BASELINE configs[3]: Examples/quad_example.py as scripted -- start [0,0,.6], goal [3,3,1.5], five waypoints at
+    tau = i/6 (the learner normalises the horizon to 1, lib/QuadAlgorithm.py:221-223), n_grid 25, theta0 = [1,.1,.1,.1,.1,.1,-1],
+    Nesterov lr 0.01 mu 0.9 with true_loss_print_flag (a second CPDP evaluation per iteration), 50 iterations.
+    First evaluation against the oracle fixture; then the whole scripted run with the learner ON THE DEVICE
+    (DeviceLearner: update, projection, stop rule and traces in k_optim_* kernels), checked against the host learner driven
+    by the same CUDA-path gradients for the first iterations and for monotone progress over the run."""
+    from lfsd_b200.optim import DeviceLearner, Learner, cpdp_grad_fn
+    fx = _fx("quadexample")
+    oc = _oc("quadrotor", 25)
+    _check_case(oc, fx, [0, 1, 2], _modes(oc))
+    oc.aux_mode = oc.MODE_BDF
+    oc.rtol_back, oc.atol_back, oc.rtol_fwd, oc.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
+    para = {"learning_rate": 0.01, "iter_num": 50, "method": "Nesterov", "mu": 0.9, "true_loss_print_flag": True}
+    args = (fx["x0"], 1.0, fx["taus"][0], fx["wp"], [0, 1, 2])
+    D = DeviceLearner(oc, *args, pdata=fx["pdata"])
+    D.load_optimization_function(para)
+    th = D.run(fx["theta"][0])
+    n = len(D.loss_trace)
+    assert n >= 5 and len(D.parameter_trace) == n + 1
+    assert D.loss_trace[-1] < 0.5 * D.loss_trace[0]      # it learns
+    assert np.isfinite(th).all() and th[0] >= 1e-8
+    H = Learner(cpdp_grad_fn(oc, *args, pdata=fx["pdata"]), 7)
+    H.load_optimization_function(dict(para, iter_num=4))
+    H.run(fx["theta"][0])
+    assert np.array_equal(np.array(H.parameter_trace), np.array(D.parameter_trace)[:5])
+    assert np.array_equal(np.array(H.loss_trace), np.array(D.loss_trace)[:4])
+    print("quad_example: %d iterations, loss %.4f -> %.4f, theta %s" % (n, D.loss_trace[0], D.loss_trace[-1], np.round(th, 4)))

@@ -10,10 +10,10 @@ from lfsd_b200.sx import _to_matrix
 from oracle import models
 
 
-@pytest.mark.parametrize("name", ["pendulum", "robotarm", "rocket", "quadrotor", "cartpole"])
+@pytest.mark.parametrize("name", ["pendulum", "robotarm", "rocket", "quadrotor", "cartpole", "pendulum_tw2"])
 def test_product_models_equal_oracle_models(name):
     oc = standard.STANDARD[name]()
-    om = getattr(models, name)()
+    om = models.pendulum_timewarp(2) if name == "pendulum_tw2" else getattr(models, name)()
     rng = np.random.default_rng(0)
     prod = [oc.dyn, oc.path_cost, oc.final_cost]
     orac = [om.dyn, sp.Matrix([om.path]), sp.Matrix([om.final])]

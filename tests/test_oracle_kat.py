@@ -90,3 +90,17 @@ def test_all_100_stored_triples_fixture(run):
     assert rel(fx["dl_cj"], grads).max() < 1e-6
     bad_fd = np.flatnonzero(rel(fx["dl_fd"], grads) > 1e-5)
     assert len(bad_fd) <= 5 and (len(bad_fd) == 0 or bad_fd.min() >= 20), bad_fd        # documented: a few late points
+
+
+def test_structured_newton_step_equals_dense():
+    """Oracle.solve(linear_solver='riccati') -- the stage-structured factorisation bench.py's CPU baseline uses -- takes the same
+    iterates as the dense assembled-KKT path (which stays the independent check of the kernels): same iteration count, same
+    inertia-correction sequence, trajectories and multipliers equal to rounding."""
+    for mk, N, th, x0 in ((models.pendulum, 10, [2.0, 1.0, 1.0], [0.0, 0.0]), (models.robotarm, 12, [5.0, 1, 1, 1, 1], [-np.pi / 2, 0, 0, 0])):
+        o = Oracle(mk(), n_grid=N)
+        a = o.solve(x0, 1.0, np.array(th), return_info=True)
+        b = o.solve(x0, 1.0, np.array(th), return_info=True, linear_solver='riccati')
+        assert a[4]["status"] == b[4]["status"] == "converged" and a[4]["iters"] == b[4]["iters"]
+        assert a[4]["reg"] == b[4]["reg"]
+        for i in (1, 2, 3):
+            assert np.abs(a[i] - b[i]).max() < 1e-10 * max(1.0, np.abs(a[i]).max())
