@@ -25,7 +25,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "CPDP OCP gradient-iterations per second (batched quadrotor OCPs, n_grid 50)"
-PORT_S_PER_OCP = 2.0      # core-seconds per OCP of the CPU port on the GPU boxes' host cores (measured; sizes the reference arm)
+PORT_S_PER_OCP = 2.4      # core-seconds per OCP of the CPU port on the GPU boxes' host cores (measured; sizes the reference arm)
 UNIT = "ocp_grad_iters/s"
 
 

@@ -8,6 +8,7 @@
 //   CPDP_LAST_ERROR()                                           0 if no launch error
 #pragma once
 #include <cstddef>
+#include <cstdlib>
 #include <cstdint>
 
 namespace CPDP_NS {
@@ -162,7 +163,11 @@ static int cpdp_aux_impl(void* ws, size_t ws_bytes, int B, int N, int S, double 
             CPDP_PREPARE_SMEM(k_riccati_rk45, ric_bytes);
             CPDP_LAUNCH(k_riccati_rk45, B, AUX_THREADS, ric_bytes, st, a);
         } else {
-            const size_t bdf_bytes = BDF_SMEM_BYTES;
+            size_t bdf_bytes = BDF_SMEM_BYTES;
+#ifdef CPDP_BDF_OCCUPANCY_KNOB
+            // developer knob (tools/prof_bdf_occupancy.py): pad the dynamic shared memory to limit the resident problems per SM
+            if (const char* pad = getenv("CPDP_BDF_SMEM_PAD")) bdf_bytes += (size_t)atol(pad);
+#endif
             CPDP_PREPARE_SMEM(k_riccati_bdf, bdf_bytes);
             CPDP_LAUNCH(k_riccati_bdf, B, BDF_THREADS, bdf_bytes, st, a);
         }

@@ -504,3 +504,30 @@ def test_quad_example_script_config(torch_mod):
     assert np.array_equal(np.array(H.parameter_trace), np.array(D.parameter_trace)[:5])
     assert np.array_equal(np.array(H.loss_trace), np.array(D.loss_trace)[:4])
     print("quad_example: %d iterations, loss %.4f -> %.4f, theta %s" % (n, D.loss_trace[0], D.loss_trace[-1], np.round(th, 4)))
+
+
+def test_integration_md_stub_runs_verbatim(torch_mod):
+    """The ctypes stub INTEGRATION.md section 2 shows a reference maintainer is executed as written (code block extracted from the
+    file), against a model without per-problem constants (pendulum) and one with (quadrotor: q = 3, the goal position)."""
+    import re
+    import types
+    import scipy.interpolate as ip
+    from lfsd_b200 import _capi
+    txt = open(os.path.join(os.path.dirname(HERE), "INTEGRATION.md")).read()
+    m = re.search(r"```python\n(# CPDP/CPDP.py — inside class COCSys, replacing the body of cocSolver.*?)```", txt, re.S)
+    assert m, "stub not found in INTEGRATION.md"
+    ns = {}
+    exec(m.group(1), ns)
+    _oc("pendulum", 10); _oc("quadrotor", 25)           # make sure the libraries exist
+    fx = _fx("pendulum")
+    me = types.SimpleNamespace(n_grid=10, steps_per_grid=4, n_state=2, n_control=1, pdata_value=None,
+                               cpdp_library=os.path.join(_capi.LIB_DIR, "libcpdp_pendulum.so"),
+                               interpolation=lambda x, y, method=1: ip.interp1d(x, y, axis=0))
+    tg, opt_sol = ns["cocSolver"](me, [0.0, 0.0], 1, fx["theta"][0])
+    assert _rel(opt_sol(tg)[:, :2], fx["X"][0]) < TRAJ_RTOL and _rel(opt_sol(tg)[:, 3:], fx["Lam"][0]) < TRAJ_RTOL
+    g = np.load(os.path.join(HERE, "golden", "quad_run.npz"))
+    me = types.SimpleNamespace(n_grid=25, steps_per_grid=4, n_state=13, n_control=4, pdata_value=g["goal_position"],
+                               cpdp_library=os.path.join(_capi.LIB_DIR, "libcpdp_quadrotor.so"),
+                               interpolation=lambda x, y, method=1: ip.interp1d(x, y, axis=0))
+    tg, opt_sol = ns["cocSolver"](me, g["ini_state"], 1.0, g["parameter_trace"][-1])
+    assert _rel(opt_sol(tg)[:, :13], g["opt_state_traj"][::4]) < TRAJ_RTOL        # the reference's stored IPOPT optimum (K2)
