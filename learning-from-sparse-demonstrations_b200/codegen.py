@@ -186,6 +186,28 @@ def generate_model_header(name, state, control, auxvar, dyn, path_cost, final_co
                  "const double* __restrict__ lam, const double* __restrict__ th, const double* __restrict__ pd, double* __restrict__ M) {\n%s\n    }" % body)
     info["pmp_nnz"] = len(assigns)
 
+    # compact set for the forward auxiliary sweep (CPDP.py:295-297 needs fx, fu, fe and, through the aux control, Hxu, Hue, Huu;
+    # not Hxx / Hxe): fx and fu as value lists in the row-major order of the FX_/FU_ COO tables, the rest dense
+    fassign = []
+    for tag, M in (("fxc", mats[0][1]), ("fuc", mats[1][1])):
+        pidx = 0
+        for i in range(M.shape[0]):
+            for j in range(M.shape[1]):
+                if M[i, j] != 0:
+                    fassign.append(("%s[%d]" % (tag, pidx), M[i, j]))
+                    pidx += 1
+    for tag, M in (("fe", mats[2][1]), ("hxu", mats[4][1]), ("hue", mats[7][1]), ("huu", mats[6][1])):
+        for i in range(M.shape[0]):
+            for j in range(M.shape[1]):
+                if M[i, j] != 0:
+                    fassign.append(("%s[%d]" % (tag, i * M.shape[1] + j), M[i, j]))
+    body, info["ops_pmp_fwd"] = _emit_body(fassign)
+    body = body.replace("mu[", "lam[")
+    parts.append("    CPDP_HD static void pmp_fwd(const double* __restrict__ x, const double* __restrict__ u, "
+                 "const double* __restrict__ lam, const double* __restrict__ th, const double* __restrict__ pd, "
+                 "double* __restrict__ fxc, double* __restrict__ fuc, double* __restrict__ fe, double* __restrict__ hxu, "
+                 "double* __restrict__ hue, double* __restrict__ huu) {\n%s\n    }" % body)
+
     hx = sp.Matrix([h]).jacobian(xs)
     body, info["ops_term"] = _emit_body([("h", h)] + [("hx[%d]" % i, hx[i]) for i in range(n)])
     parts.append("    CPDP_HD static void term(const double* __restrict__ x, const double* __restrict__ th, const double* __restrict__ pd, "

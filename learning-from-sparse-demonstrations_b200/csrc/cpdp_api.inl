@@ -157,7 +157,7 @@ static int cpdp_aux_impl(void* ws, size_t ws_bytes, int B, int N, int S, double 
     a.taus = taus; a.taus_stride = taus_stride; a.wp = wp;
     a.loss = loss; a.dtheta = dtheta; a.solve_status = solve_status; a.aux_status = aux_status; a.counters = counters;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t ric_bytes = rk_smem_bytes<false>(), fwd_bytes = rk_smem_bytes<true>();
+    const size_t ric_bytes = rk_smem_bytes<false>(), fwd_bytes = FW_SMEM_BYTES;
     if (phases & 1) {
         if (mode == 0) {
             CPDP_PREPARE_SMEM(k_riccati_rk45, ric_bytes);
@@ -174,7 +174,7 @@ static int cpdp_aux_impl(void* ws, size_t ws_bytes, int B, int N, int S, double 
     }
     if (phases & 2) {
         CPDP_PREPARE_SMEM(k_aux_forward, fwd_bytes);
-        CPDP_LAUNCH(k_aux_forward, B, AUX_THREADS, fwd_bytes, st, a);
+        CPDP_LAUNCH(k_aux_forward, B, FW_THREADS, fwd_bytes, st, a);
     }
     return CPDP_LAST_ERROR();
 }

@@ -617,87 +617,6 @@ CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_riccati_rk45(AuxArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_aux_forward: X(0)=0, RK45 per interval (CPDP.py:352-378), aux control at the nodes, then the loss closure
-//   L = sum_i |wp_i - y(x(tau_i))|^2 ,  dL = sum_i (y - wp_i)' Sel X(tau_i)   (no factor 2, as in the reference).
-// ------------------------------------------------------------------------------------------------
-CPDP_GLOBAL void __launch_bounds__(AUX_THREADS) k_aux_forward(AuxArgs a) {
-    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    if (a.aux_status[b] != 0) {
-        if (tid == 0) a.loss[b] = 0.0;
-        for (int i = tid; i < NP; i += nt) a.dtheta[(size_t)b * NP + i] = 0.0;
-        return;
-    }
-    RK_LAYOUT(true);
-    aux_shared_fill(s);
-    aux_tables(s, (int*)s.ti + 2 * NT);
-    double* y = w.y; double* yn = w.yn; double* ys = w.ys; double* K = w.K; double* tms = w.tms;
-    const int N = a.N;
-    AuxProblem p;
-    p.X = a.X + (size_t)b * (N + 1) * NX; p.U = a.U + (size_t)b * (N + 1) * NU; p.Lam = a.Lam + (size_t)b * (N + 1) * NX;
-    p.th = a.theta + (size_t)b * a.theta_stride; p.pd = a.pdata + (size_t)b * NQ; p.PW = a.PW + (size_t)b * (N + 1) * NYR; p.dt = a.T / N; p.N = N;
-    double* Xa = a.Xa + (size_t)b * (N + 1) * NYF;
-    double* Ua = a.Ua + (size_t)b * (N + 1) * NU * NP;
-    for (int q = tid; q < NYF; q += nt) { y[q] = 0.0; Xa[q] = 0.0; }
-    __syncthreads();
-    int nrhs = 0, nsteps = 0, st = 0;
-    for (int k = 0; k <= N && st == 0; ++k) {
-        // aux control at node k
-        if (tid == 0) tms[0] = p.dt * k;
-        if (!rk_prepare<true>(p, 1)) { st = 2; break; }
-        for (int i = tid; i < NU * NP; i += nt) {
-            const int aa = i / NP, kk = i % NP;
-            double acc = s.HZ[i];
-            for (int c = 0; c < NX; ++c) acc += s.HY[aa * NX + c] * y[c * NP + kk];
-            Ua[(size_t)k * NU * NP + i] = acc;
-        }
-        __syncthreads();
-        if (k == N) break;
-        st = rk45_interval<true, NYF>(s, p, p.dt * k, p.dt * (k + 1), a.rtol_f, a.atol_f, y, yn, ys, K, tms, nrhs, nsteps);
-        for (int q = tid; q < NYF; q += nt) Xa[(size_t)(k + 1) * NYF + q] = y[q];
-        __syncthreads();
-    }
-    if (tid == 0) { a.aux_status[b] = st; a.counters[b * NCOUNTERS + 2] = nrhs; a.counters[b * NCOUNTERS + 3] = nsteps; }
-    // ---- loss and gradient: thread 0 the loss, parameter i by thread i % nt (strided: r may exceed the CTA size).
-    //      A waypoint time outside [0, T] is an error (scipy's interp1d raises ValueError in the reference): status 5.
-    const double* taus = a.taus + (size_t)b * a.taus_stride;
-    const double* wp = a.wp + (size_t)b * a.W * a.D;
-    bool tau_bad = false;
-    for (int w = 0; w < a.W; ++w) if (!(taus[w] >= 0.0 && taus[w] <= p.dt * N)) tau_bad = true;
-    if (tau_bad && st == 0) { st = 5; if (tid == 0) a.aux_status[b] = 5; }
-    if (tid == 0) {
-        double lo_ = 0.0;
-        for (int w = 0; w < a.W && st == 0; ++w) {
-            const double t = taus[w];
-            const int lo = interp_lo(t, p.dt, N);
-            const double xlo = p.dt * lo, xhi = p.dt * (lo + 1);
-            for (int d = 0; d < a.D; ++d) {
-                const int si = a.sel[d];
-                const double yv = interp_val(p.X[(size_t)lo * NX + si], p.X[(size_t)(lo + 1) * NX + si], xlo, xhi, t);
-                const double diff = yv - wp[(size_t)w * a.D + d];
-                lo_ += diff * diff;
-            }
-        }
-        a.loss[b] = lo_;
-    }
-    for (int i = tid; i < NP; i += nt) {
-        double acc = 0.0;
-        for (int w = 0; w < a.W && st == 0; ++w) {
-            const double t = taus[w];
-            const int lo = interp_lo(t, p.dt, N);
-            const double xlo = p.dt * lo, xhi = p.dt * (lo + 1);
-            for (int d = 0; d < a.D; ++d) {
-                const int si = a.sel[d];
-                const double yv = interp_val(p.X[(size_t)lo * NX + si], p.X[(size_t)(lo + 1) * NX + si], xlo, xhi, t);
-                const double diff = yv - wp[(size_t)w * a.D + d];
-                const double xa = interp_val(Xa[(size_t)lo * NYF + si * NP + i], Xa[(size_t)(lo + 1) * NYF + si * NP + i], xlo, xhi, t);
-                acc += diff * xa;
-            }
-        }
-        a.dtheta[(size_t)b * NP + i] = acc;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // k_reduce_tree: canonical pairwise (binary-tree over the problem index) sum of rows [loss | dL/dtheta].
 // The tree shape depends only on the TOTAL number of rows, never on how they were sharded over GPUs, so the
 // result is bit-identical for 1/2/4/8 ranks (rows are all-gathered before this kernel).

@@ -388,9 +388,16 @@ CPDP_D int bdf_top_bit(unsigned m) {            // index of the highest set bit 
     return b;
 #endif
 }
+// 1 / sqrt(x) for a positive, normal x to ~1 ulp: hardware seed + two Newton steps (the reflectors of the bulge chase are built
+// from it: any consistent scaling gives an orthogonal reflector to rounding)
 CPDP_D double bdf_rsqrt(double x) {
 #ifdef __CUDACC__
-    return rsqrt(x);
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    r = fma(r, fma(-hx * r, r, 0.5), r);
+    r = fma(r, fma(-hx * r, r, 0.5), r);
+    return r;
 #else
     return 1.0 / sqrt(x);
 #endif
@@ -511,7 +518,7 @@ CPDP_D bool schur_real_w0(double* sm, double* H, double* Z, double* vb) {
                 const double sgn = (p < 0.0) ? -1.0 : 1.0;
                 const double s = sgn * (sig * rs);
                 const double xx = 1.0 + fabs(p) * rs, yy = q * rs * sgn, zz = r * rs * sgn;
-                const double ixx = 1.0 / xx;
+                const double ixx = bdf_rcp(xx);                          // xx in [1, 2]
                 const double qn = yy * ixx, rn = zz * ixx;
                 if (lane >= k && lane < n) {
                     double pp = h_(k, lane) + qn * h_(k + 1, lane);
@@ -717,21 +724,30 @@ CPDP_D void bdf_sweep(double* sm, const double c) {
     const int tid = threadIdx.x;
     const double* T2 = sm + bo::T2S; double* Y = sm + bo::Y2; const double* PVm = sm + bo::PV;
     const int e = tid >> 2, sub = tid & 3;
-    CPDP_LOOP for (int d = 2 * (n - 1); d >= 0; --d) {
-        const int ilo = (d > n - 1) ? d - (n - 1) : 0;
-        const int i = ilo + e, j = d - i;
-        const bool valid = (i <= j);
+    // The four operand addresses of a lane move by constant strides from one anti-diagonal to the next (two regimes: above the
+    // main anti-diagonal the row index of the entry drops, below it the column index does), so they are carried in registers and
+    // stepped -- no address arithmetic between the barrier and the loads.  Lanes without an entry run on entry (0, 0), unstored.
+    int d = 2 * (n - 1);
+    int i = (n - 1) + e, j = d - i;                              // entry e of the first anti-diagonal (only e = 0 exists there)
+    CPDP_LOOP for (; d >= 0; --d) {
+        const bool valid = (i <= j) && (i >= 0);
         const int ic = valid ? i : 0, jc = valid ? j : 0;
         const double* ta = T2 + 2 * (ic * TW + sub); const double* ya = Y + 2 * ((ic + 1 + sub) * n + jc);
         const double* tb = T2 + 2 * (jc * TW + sub); const double* yb = Y + 2 * ((jc + 1 + sub) * n + ic);
-        double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;
+        const double* cvp = Y + 2 * (ic * n + jc); const double* pvp = PVm + 2 * (ic * n + jc);
+        double pr[2 * SWQ], pi_[2 * SWQ];
         BDF_UNROLL for (int m = 0; m < SWQ; ++m) {
             const auto t1 = BDF_LD2(ta + 8 * m), y1 = BDF_LD2(ya + 8 * m * n);
             const auto t2 = BDF_LD2(tb + 8 * m), y2 = BDF_LD2(yb + 8 * m * n);
-            ar += t1.x * y1.x - t1.y * y1.y; ai += t1.x * y1.y + t1.y * y1.x;
-            br += t2.x * y2.x - t2.y * y2.y; bi += t2.x * y2.y + t2.y * y2.x;
+            pr[m] = t1.x * y1.x - t1.y * y1.y; pi_[m] = t1.x * y1.y + t1.y * y1.x;
+            pr[SWQ + m] = t2.x * y2.x - t2.y * y2.y; pi_[SWQ + m] = -(t2.x * y2.y + t2.y * y2.x);      // conj S(j, i)
         }
-        ar += br; ai -= bi;
+        const auto cv = BDF_LD2(cvp), pv = BDF_LD2(pvp);
+        // pairwise tree over the 2 SWQ products
+        BDF_UNROLL for (int w = 1; w < 2 * SWQ; w *= 2) {
+            BDF_UNROLL for (int m = 0; m + w < 2 * SWQ; m += 2 * w) { pr[m] += pr[m + w]; pi_[m] += pi_[m + w]; }
+        }
+        double ar = pr[0], ai = pi_[0];
 #ifdef __CUDACC__
         ar += __shfl_xor_sync(0xffffffffu, ar, 1); ai += __shfl_xor_sync(0xffffffffu, ai, 1);
         ar += __shfl_xor_sync(0xffffffffu, ar, 2); ai += __shfl_xor_sync(0xffffffffu, ai, 2);
@@ -746,12 +762,13 @@ CPDP_D void bdf_sweep(double* sm, const double c) {
         }
 #endif
         if (valid && sub == 0) {
-            const auto cv = BDF_LD2(Y + 2 * (i * n + j)), pv = BDF_LD2(PVm + 2 * (i * n + j));
             const double rr = cv.x - c * ar, ri = cv.y - c * ai;
             const double yr = rr * pv.x - ri * pv.y, yi = rr * pv.y + ri * pv.x;
             BDF_ST2(Y + 2 * (i * n + j), yr, (i == j) ? 0.0 : yi);
             if (i != j) BDF_ST2(Y + 2 * (j * n + i), yr, -yi);
         }
+        // next anti-diagonal: d > n-1: the first row of the diagonal drops by one (i - 1, same j); else the column does
+        if (d > n - 1) --i; else --j;
         BDF_SYNC();
     }
 }

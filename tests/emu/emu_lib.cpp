@@ -12,6 +12,7 @@
 #include "cpdp_kernels.cuh"
 #include "cpdp_aux.cuh"
 #include "cpdp_bdf.cuh"
+#include "cpdp_fwd.cuh"
 #include "cpdp_optim.cuh"
 
 thread_local cpdp_emu_dim3 threadIdx;
