@@ -251,6 +251,18 @@ def test_full_size_properties(torch_mod):
     fx = _fx("quad50")
     nb = fx["X"].shape[0]
     assert _rel(X[:nb], fx["X"]) < TRAJ_RTOL          # first problems of the batch are the oracle fixture
+    # the sweeps at full size: every problem integrates, the first ones equal the fixture, the reduced row reports no failure
+    oc.aux_mode = oc.MODE_BDF
+    oc.rtol_back, oc.atol_back, oc.rtol_fwd, oc.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
+    aux = oc.auxSysSolverBatch(sol, qb["taus"], qb["wp"], qb["sel"])
+    ast = _np(aux["aux_status"])
+    print("4096 quadrotor OCPs: solver status", np.bincount(st, minlength=5).tolist(), "aux status", np.bincount(ast, minlength=6).tolist())
+    assert (ast[ok] == 0).all()
+    assert np.isfinite(_np(aux["dtheta"])).all() and (_np(aux["loss"]) >= 0).all()
+    for b in range(nb):
+        assert _rel(_np(aux["dtheta"])[b], fx["dl_asshipped_cj"][b]) < GRAD_RTOL
+    full = _np(oc.reduceRows(oc.packRows(sol, aux)))
+    assert full[-1] == float((~ok).sum()) and np.allclose(full[0], _np(aux["loss"]).sum(), rtol=1e-12)
 
 
 def test_stored_run_learning_trace(torch_mod):
@@ -292,7 +304,11 @@ def test_robotarm_batch256_properties(torch_mod):
     sol = oc.cocSolverBatch(ab["x0"], 1.0, ab["theta"])
     st = _np(sol["status"])
     ok = st == 1
-    assert ok.mean() > 0.95, np.bincount(st)
+    print("robot arm, 256 random theta0: solver status counts [running, converged, max_iter, linesearch, numeric] =",
+          np.bincount(st, minlength=5).tolist())
+    # observed on the B200: 246 converged, 10 line-search failures (the filter line search has no restoration phase; the
+    # reference would carry on with whatever IPOPT returned) -- deterministic, so the bound is the observation
+    assert (~ok).sum() <= 10, np.bincount(st)
     assert _np(sol["kkt"])[ok].max() < 1e-10
     X, U = _np(sol["X"]), _np(sol["U"])
     assert np.abs(X[ok][:, 0, :] - ab["x0"][ok]).max() < 1e-12
@@ -306,7 +322,8 @@ def test_robotarm_batch256_properties(torch_mod):
         oc.rtol_back, oc.atol_back, oc.rtol_fwd, oc.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
         aux = oc.auxSysSolverBatch(sol, ab["taus"], ab["wp"], ab["sel"])
         ast = _np(aux["aux_status"])
-        assert (ast[ok] == 0).mean() > 0.98, np.bincount(ast[ok])
+        print("robot arm, sweep mode %d: aux status counts over the converged problems =" % mode, np.bincount(ast[ok], minlength=6).tolist())
+        assert (ast[ok] != 0).sum() == 0, np.bincount(ast[ok])          # observed: no failed sweep in either mode
         good = ok & (ast == 0)
         assert np.isfinite(_np(aux["dtheta"])[good]).all() and (_np(aux["loss"])[good] >= 0).all()
         tag = "asshipped_cj" if mode != oc.MODE_RK45 else "rk45"
@@ -324,7 +341,8 @@ def test_rocket_batch1024_properties(torch_mod):
     rb = synthetic.rocket_batch(1024)
     demo = oc.cocSolverBatch(rb["x0"], 3.0, rb["theta_true"])
     okd = _np(demo["status"]) == 1
-    assert okd[:2].all() and okd.mean() > 0.95, np.bincount(_np(demo["status"]))
+    print("rocket, 1024 demos at theta*: solver status counts =", np.bincount(_np(demo["status"]), minlength=5).tolist())
+    assert okd[:2].all() and (~okd).sum() <= 1, np.bincount(_np(demo["status"]))      # observed: 1023 converged, 1 line-search failure
     Xd = _np(demo["X"])[okd]
     x0 = rb["x0"][okd]
     quat_norm = np.linalg.norm(Xd[:, :, 6:10], axis=2)
@@ -336,14 +354,16 @@ def test_rocket_batch1024_properties(torch_mod):
     sol = oc.cocSolverBatch(x0, 3.0, rb["theta0"])
     st = _np(sol["status"])
     ok = st == 1
-    assert ok[:2].all() and ok.mean() > 0.95, np.bincount(st)
+    print("rocket, learning batch at theta0: solver status counts =", np.bincount(st, minlength=5).tolist())
+    assert ok.all(), np.bincount(st)                                    # observed: all 1023 converge
     assert _np(sol["kkt"])[ok].max() < 1e-10
     assert _rel(_np(sol["X"])[:2], fx["X"]) < TRAJ_RTOL
     oc.aux_mode = oc.MODE_BDF if _has_bdf(oc) else oc.MODE_RK45
     oc.rtol_back, oc.atol_back, oc.rtol_fwd, oc.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
     aux = oc.auxSysSolverBatch(sol, taus, wp, rb["sel"])
     ast = _np(aux["aux_status"])
-    assert (ast[ok] == 0).mean() > 0.98, np.bincount(ast[ok])
+    print("rocket: aux status counts over the converged problems =", np.bincount(ast[ok], minlength=6).tolist())
+    assert (ast[ok] != 0).sum() == 0, np.bincount(ast[ok])              # observed: no failed sweep
     tag = "asshipped_cj" if _has_bdf(oc) else "rk45"
     for b in range(2):      # waypoints come from the GPU's own demo solve (1e-9 from the oracle's): 10 x the gradient tolerance
         assert _rel(_np(aux["dtheta"])[b], fx["dl_" + tag][b]) < 10 * GRAD_RTOL, (b, _np(aux["dtheta"])[b], fx["dl_" + tag][b])
@@ -531,3 +551,27 @@ def test_integration_md_stub_runs_verbatim(torch_mod):
                                interpolation=lambda x, y, method=1: ip.interp1d(x, y, axis=0))
     tg, opt_sol = ns["cocSolver"](me, g["ini_state"], 1.0, g["parameter_trace"][-1])
     assert _rel(opt_sol(tg)[:, :13], g["opt_state_traj"][::4]) < TRAJ_RTOL        # the reference's stored IPOPT optimum (K2)
+
+
+@pytest.mark.parametrize("method", ["Adam", "Nadam", "AMSGrad", "Vanilla"])
+def test_device_learner_other_rules_match_host_learner(torch_mod, method):
+    """the learner's other update rules (lib/QuadAlgorithm.py:454-466, 497-578) on the device (k_optim_post around
+    the CUDA gradient iteration) give the traces of the host restatement driven by the same gradients, bit for bit."""
+    from lfsd_b200.optim import DeviceLearner, Learner, cpdp_grad_fn
+    fx = _fx("pendulum")
+    oc = _oc("pendulum", 10)
+    oc.aux_mode = oc.MODE_BDF
+    oc.rtol_back, oc.atol_back, oc.rtol_fwd, oc.atol_fwd = 1e-3, 1e-6, 1e-3, 1e-6
+    para = {"learning_rate": 0.02, "iter_num": 6, "method": method, "beta_1": 0.9, "beta_2": 0.999, "epsilon": 1e-8}
+    x0 = np.zeros((2, 2))
+    wp = np.tile(fx["wp"][0][None], (2, 1, 1)) * np.array([1.0, 1.1]).reshape(2, 1, 1)
+    args = (x0, 1.0, fx["taus"][0], wp, [0])
+    H = Learner(cpdp_grad_fn(oc, *args), 3)
+    H.load_optimization_function(para)
+    H.run(fx["theta"][0])
+    D = DeviceLearner(oc, *args)
+    D.load_optimization_function(para)
+    D.run(fx["theta"][0])
+    assert len(H.loss_trace) == len(D.loss_trace) >= 2
+    assert np.array_equal(np.array(H.parameter_trace), np.array(D.parameter_trace)), method
+    assert np.array_equal(np.array(H.loss_trace), np.array(D.loss_trace))
