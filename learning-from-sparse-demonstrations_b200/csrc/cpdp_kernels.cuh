@@ -220,7 +220,8 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
     CPDP_SHARED double s_u[KPC][NU];
     CPDP_SHARED double s_th[KPC][NP];
     CPDP_SHARED double s_pd[KPC][NQT > 0 ? NQT : 1];
-    CPDP_SHARED double s_S[KPC][NZ][NX];
+    constexpr int SXS = (NX + 1) & ~1;                 // even row length: the Hessian accumulation reads the rows with 128-bit loads
+    CPDP_SHARED __align__(16) double s_S[KPC][NZ][SXS];
     CPDP_SHARED int s_gi[KPC];                 // global interval index b*N+k of each slot, -1 if none
     const int tid = threadIdx.x;
     const int kk = tid / NZ, j = tid % NZ;
@@ -283,7 +284,17 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
                     for (int i = 0; i < NZ; ++i) {
                         double acc = (i >= NX) ? hz[i] : 0.0;
                         const double* col = s_S[kk][i];
+#ifdef __CUDACC__
+#pragma unroll
+                        for (int e = 0; e + 1 < NX; e += 2) {
+                            const double2 c2 = *reinterpret_cast<const double2*>(col + e);
+                            acc += c2.x * hz[e];
+                            acc += c2.y * hz[e + 1];
+                        }
+                        if (NX & 1) acc += col[NX - 1] * hz[NX - 1];
+#else
                         for (int e = 0; e < NX; ++e) acc += col[e] * hz[e];
+#endif
                         Hc[i] += acc;
                     }
                     const double cb = bco[st] * DT;
@@ -379,13 +390,47 @@ CPDP_HD void chol_solve(const double* L, double* b) {
 //  3. IPOPT filter line search (one thread per interval re-integrates the RK4 map).
 //  4. Primal / dual update.
 // ------------------------------------------------------------------------------------------------
-#ifndef CPDP_NEWTON_THREADS
-#define CPDP_NEWTON_THREADS 64
+// Shape (round 2): ONE WARP per problem; lane j < NZ owns column j of the stage matrices ([A B], T = V [A B], Q) in
+// registers, every product is "matrix in shared memory (broadcast loads, contraction index rolled) times my column" with NX / NZ
+// independent accumulators -- the first version ran 64-thread CTAs through rolled shared-memory dot products with ten CTA
+// barriers per stage (1.2 ms per round at any batch size: latency bound).  All sums are taken in the first version's order.
+constexpr int NEWTON_THREADS = 32;
+static_assert(NZ <= 32, "k_newton_step maps one lane per column of the stage-wise KKT blocks");
+constexpr int NZS = NZ | 1;              // odd row strides: conflict-free row reads by lane
+constexpr int NXS = NX | 1;
+
+#ifdef __CUDACC__
+#define NWT_SYNC() __syncwarp()
+#define NWT_UNROLL _Pragma("unroll")
+#else
+#define NWT_SYNC() __syncthreads()
+#define NWT_UNROLL
 #endif
-constexpr int NEWTON_THREADS = CPDP_NEWTON_THREADS;
+
+// out[i] += sum_k AT[k * as + i] * x[k * xs], i < NOUT: contraction rolled, NOUT independent accumulators (ascending k)
+template <int NOUT>
+CPDP_D void nwt_mac(const double* __restrict__ AT, const int as, const double* __restrict__ x, const int xs, const int nk, double (&out)[NOUT]) {
+    CPDP_LOOP for (int k = 0; k < nk; ++k) {
+        const double xk = x[k * xs];
+        NWT_UNROLL for (int i = 0; i < NOUT; ++i) out[i] += AT[k * as + i] * xk;
+    }
+}
+
+CPDP_D double nwt_reduce(double v, double* red, bool is_max) {
+#ifdef __CUDACC__
+    (void)red;
+    NWT_UNROLL for (int o = 16; o > 0; o >>= 1) {
+        const double x = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmax(v, x) : (v + x);
+    }
+    return v;
+#else
+    return block_reduce(v, red, is_max);
+#endif
+}
 
 CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = threadIdx.x, nt = NEWTON_THREADS;
     const int N = a.N;
     const double DT = a.T / a.N / a.S;
     const double* th = theta_of(a, b);
@@ -401,16 +446,18 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
     double* vs = a.vs + (size_t)b * (N + 1) * NX;
     const size_t ib = (size_t)b * N;
 
-    CPDP_SHARED double red[NEWTON_THREADS + 1];
+    CPDP_SHARED double red[66];
     CPDP_SHARED double s_hx[NX], s_hxx[NX * NX], s_hxe[NX * NP];
-    CPDP_SHARED double s_V[NX * NX], s_v[NX], s_vt[NX];
-    CPDP_SHARED double s_AB[NX * NZ], s_T[NX * NZ], s_Q[NZ * NZ], s_qv[NZ], s_gq[NZ];
-    CPDP_SHARED double s_L[NU * NU], s_K[NU * NX], s_kf[NU];
+    CPDP_SHARED double s_V[NX * NXS], s_v[NX], s_vt[NX];          // value function of the stage being eliminated (V symmetric)
+    CPDP_SHARED double s_AB[NX * NZS], s_T[NX * NZS], s_Q[NZ * NZS];
+    CPDP_SHARED double s_L[NU * NU], s_K[NU * NXS], s_kf[NU], s_dx[NX], s_du[NU], s_dk[NX], s_lk[NX];
     CPDP_SHARED double s_h;
     CPDP_SHARED int s_flag;
+    const bool isZ = lane < NZ, isX = lane < NX;
+    const int jz = isZ ? lane : 0, jx = isX ? lane : 0;
 
     // ---- terminal cost derivatives, defect of the initial condition
-    if (tid == 0) {
+    if (lane == 0) {
         double h;
         PdBuf pdb;
         const double* pd = pd_at(pd0, grid_time(a.T, N, N), pdb);
@@ -418,28 +465,28 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
         Model::term2(X + (size_t)N * NX, th, pd, s_hxx, s_hxe);
         s_h = h;
     }
-    for (int i = tid; i < NX; i += nt) dfc[i] = a.x0[(size_t)b * NX + i] - X[i];
-    __syncthreads();
+    for (int i = lane; i < NX; i += nt) dfc[i] = a.x0[(size_t)b * NX + i] - X[i];
+    NWT_SYNC();
 
     // ---- KKT error and objective
     double e = 0.0, Jp = 0.0, g1 = 0.0;
-    for (int k = tid; k < N; k += nt) {
+    for (int k = lane; k < N; k += nt) {
         const double* g = a.gL + (ib + k) * NZ;
         for (int i = 0; i < NX; ++i) e = fmax(e, fabs(g[i] - Lam[(size_t)k * NX + i]));
         for (int i = 0; i < NU; ++i) e = fmax(e, fabs(g[NX + i]));
         Jp += a.cost[ib + k];
     }
-    for (int i = tid; i < (N + 1) * NX; i += nt) { e = fmax(e, fabs(dfc[i])); g1 += fabs(dfc[i]); }
-    for (int i = tid; i < NX; i += nt) e = fmax(e, fabs(s_hx[i] - Lam[(size_t)N * NX + i]));
-    const double kkt = block_reduce(e, red, true);
-    const double J0 = block_reduce(Jp, red, false) + s_h;
-    g1 = block_reduce(g1, red, false);
-    if (tid == 0) { a.kkt[b] = kkt; a.J[b] = J0; }
+    for (int i = lane; i < (N + 1) * NX; i += nt) { e = fmax(e, fabs(dfc[i])); g1 += fabs(dfc[i]); }
+    for (int i = lane; i < NX; i += nt) e = fmax(e, fabs(s_hx[i] - Lam[(size_t)N * NX + i]));
+    const double kkt = nwt_reduce(e, red, true);
+    const double J0 = nwt_reduce(Jp, red, false) + s_h;
+    g1 = nwt_reduce(g1, red, false);
+    if (lane == 0) { a.kkt[b] = kkt; a.J[b] = J0; }
     const int it = a.iters[b];
-    if (!(kkt == kkt)) { if (tid == 0) a.status[b] = ST_NUMERIC; }
+    if (!(kkt == kkt)) { if (lane == 0) a.status[b] = ST_NUMERIC; }
     if (kkt < a.tol || it >= a.max_iter || !(kkt == kkt)) {
-        if (tid == 0 && kkt == kkt) a.status[b] = (kkt < a.tol) ? ST_CONVERGED : ST_MAXITER;
-        for (int i = tid; i < NU; i += nt) U[(size_t)N * NU + i] = U[(size_t)(N - 1) * NU + i];   // CPDP.py:191
+        if (lane == 0 && kkt == kkt) a.status[b] = (kkt < a.tol) ? ST_CONVERGED : ST_MAXITER;
+        for (int i = lane; i < NU; i += nt) U[(size_t)N * NU + i] = U[(size_t)(N - 1) * NU + i];   // CPDP.py:191
         return;
     }
 
@@ -448,167 +495,194 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
     double delta = 0.0;
     int attempt = 0;
     while (true) {
-        for (int i = tid; i < NX * NX; i += nt) s_V[i] = s_hxx[i] + ((i / NX == i % NX) ? delta : 0.0);
-        for (int i = tid; i < NX; i += nt) s_v[i] = s_hx[i];
-        if (tid == 0) s_flag = 0;
-        __syncthreads();
-        for (int i = tid; i < NX * NX; i += nt) Vs[(size_t)N * NX * NX + i] = s_V[i];
-        for (int i = tid; i < NX; i += nt) vs[(size_t)N * NX + i] = s_v[i];
+        if (isX) {
+            NWT_UNROLL for (int i = 0; i < NX; ++i) {
+                const double v = s_hxx[i * NX + jx] + ((i == jx) ? delta : 0.0);
+                s_V[i * NXS + jx] = v;
+                Vs[(size_t)N * NX * NX + i * NX + jx] = v;
+            }
+            s_v[jx] = s_hx[jx];
+            vs[(size_t)N * NX + jx] = s_hx[jx];
+        }
+        if (lane == 0) s_flag = 0;
+        NWT_SYNC();
         for (int k = N - 1; k >= 0; --k) {
             const double* ABg = a.AB + (ib + k) * NX * NZ;
             const double* Hg = a.H + (ib + k) * NZ * NZ;
             const double* gLg = a.gL + (ib + k) * NZ;
             const double* dk1 = dfc + (size_t)(k + 1) * NX;
             const double* lk1 = Lam + (size_t)(k + 1) * NX;
-            for (int i = tid; i < NX * NZ; i += nt) s_AB[i] = ABg[i];
-            // vt = v + V d_{k+1}
-            for (int i = tid; i < NX; i += nt) {
-                double acc = s_v[i];
-                for (int c = 0; c < NX; ++c) acc += s_V[i * NX + c] * dk1[c];
-                s_vt[i] = acc;
+            // my column of [A B]; vt = v + V d_{k+1}
+            // (every global operand of the stage is fetched up front, in one batch of independent loads: the stage loop is a
+            //  chain of short dependent phases, an L2 round trip inside any of them is paid 50 times per problem and round)
+            double ab[NX], hq[NZ];
+            NWT_UNROLL for (int e2 = 0; e2 < NX; ++e2) ab[e2] = isZ ? ABg[e2 * NZ + jz] : 0.0;
+            NWT_UNROLL for (int r_ = 0; r_ < NZ; ++r_) hq[r_] = isZ ? 0.5 * (Hg[r_ * NZ + jz] + Hg[jz * NZ + r_]) : 0.0;
+            const double gl = isZ ? gLg[jz] : 0.0;
+            if (isX) { s_dk[jx] = dk1[jx]; s_lk[jx] = lk1[jx]; }
+            NWT_UNROLL for (int e2 = 0; e2 < NX; ++e2) if (isZ) s_AB[e2 * NZS + jz] = ab[e2];
+            NWT_SYNC();
+            if (isX) {
+                double acc = s_v[jx];
+                NWT_UNROLL for (int c = 0; c < NX; ++c) acc += s_V[jx * NXS + c] * s_dk[c];
+                s_vt[jx] = acc;
             }
-            __syncthreads();
-            // T = V [A B];  gq = gL - [A B]' lam_{k+1}
-            for (int i = tid; i < NX * NZ; i += nt) {
-                const int r_ = i / NZ, c = i % NZ;
-                double acc = 0.0;
-                for (int e2 = 0; e2 < NX; ++e2) acc += s_V[r_ * NX + e2] * s_AB[e2 * NZ + c];
-                s_T[i] = acc;
-            }
-            for (int c = tid; c < NZ; c += nt) {
-                double acc = gLg[c];
-                for (int e2 = 0; e2 < NX; ++e2) acc -= s_AB[e2 * NZ + c] * lk1[e2];
-                s_gq[c] = acc;
-            }
-            __syncthreads();
-            // Q = H + delta I + [A B]' T ; qv = gq + [A B]' vt
-            for (int i = tid; i < NZ * NZ; i += nt) {
-                const int r_ = i / NZ, c = i % NZ;
-                double acc = 0.5 * (Hg[r_ * NZ + c] + Hg[c * NZ + r_]) + ((r_ == c) ? delta : 0.0);
-                for (int e2 = 0; e2 < NX; ++e2) acc += s_AB[e2 * NZ + r_] * s_T[e2 * NZ + c];
-                s_Q[i] = acc;
-            }
-            for (int c = tid; c < NZ; c += nt) {
-                double acc = s_gq[c];
-                for (int e2 = 0; e2 < NX; ++e2) acc += s_AB[e2 * NZ + c] * s_vt[e2];
-                s_qv[c] = acc;
-                a.gq[(ib + k) * NZ + c] = s_gq[c];
-            }
-            __syncthreads();
+            NWT_SYNC();
+            // T[:, j] = V [A B][:, j]   (V symmetric: V[e][i] = V[i][e] is its own contraction-major operand)
+            double t[NX];
+            NWT_UNROLL for (int i = 0; i < NX; ++i) t[i] = 0.0;
+            nwt_mac<NX>(s_V, NXS, s_AB + jz, NZS, NX, t);
+            // gq[j] = gL[j] - [A B][:, j]' lam_{k+1};  qv[j] = gq[j] + [A B][:, j]' vt
+            double gqj = gl;
+            NWT_UNROLL for (int e2 = 0; e2 < NX; ++e2) gqj -= ab[e2] * s_lk[e2];
+            double qvj = gqj;
+            NWT_UNROLL for (int e2 = 0; e2 < NX; ++e2) qvj += ab[e2] * s_vt[e2];
+            if (isZ) { NWT_UNROLL for (int e2 = 0; e2 < NX; ++e2) s_T[e2 * NZS + jz] = t[e2]; a.gq[(ib + k) * NZ + jz] = gqj; }
+            // Q[:, j] = sym(H)[:, j] + delta e_j + [A B]' T[:, j]
+            double q[NZ];
+            NWT_UNROLL for (int r_ = 0; r_ < NZ; ++r_) q[r_] = hq[r_] + ((isZ && r_ == jz) ? delta : 0.0);
+            nwt_mac<NZ>(s_AB, NZS, s_T + jz, NZS, NX, q);          // (reads my own column of T: no barrier needed)
+            if (isZ) { NWT_UNROLL for (int r_ = 0; r_ < NZ; ++r_) s_Q[r_ * NZS + jz] = q[r_]; }
+            NWT_SYNC();
             // Quu = L L'
-            if (tid == 0) {
+            if (lane == 0) {
                 for (int r_ = 0; r_ < NU; ++r_)
                     for (int c = 0; c < NU; ++c)
-                        s_L[r_ * NU + c] = 0.5 * (s_Q[(NX + r_) * NZ + NX + c] + s_Q[(NX + c) * NZ + NX + r_]);
+                        s_L[r_ * NU + c] = 0.5 * (s_Q[(NX + r_) * NZS + NX + c] + s_Q[(NX + c) * NZS + NX + r_]);
                 if (!chol_inplace<NU>(s_L)) s_flag = 1;
             }
-            __syncthreads();
+            NWT_SYNC();
             if (s_flag) break;
-            // K = -Quu^{-1} Qux (columns), kf = -Quu^{-1} qu
-            for (int c = tid; c <= NX; c += nt) {
+            // K = -Quu^{-1} Qux (my column), kf = -Quu^{-1} qu (lane NX, which holds qv[NX..] below)
+            if (isX) {
                 double rhs[NU];
-                if (c < NX) { for (int r_ = 0; r_ < NU; ++r_) rhs[r_] = 0.5 * (s_Q[(NX + r_) * NZ + c] + s_Q[c * NZ + NX + r_]); }
-                else { for (int r_ = 0; r_ < NU; ++r_) rhs[r_] = s_qv[NX + r_]; }
+                NWT_UNROLL for (int r_ = 0; r_ < NU; ++r_) rhs[r_] = 0.5 * (q[NX + r_] + s_Q[jx * NZS + NX + r_]);
                 chol_solve<NU>(s_L, rhs);
-                if (c < NX) { for (int r_ = 0; r_ < NU; ++r_) s_K[r_ * NX + c] = -rhs[r_]; }
-                else { for (int r_ = 0; r_ < NU; ++r_) s_kf[r_] = -rhs[r_]; }
+                NWT_UNROLL for (int r_ = 0; r_ < NU; ++r_) { s_K[r_ * NXS + jx] = -rhs[r_]; a.Kf[(ib + k) * NU * NX + r_ * NX + jx] = -rhs[r_]; }
             }
-            __syncthreads();
+            // qv of the control rows travels through shared memory to one lane
+            if (lane >= NX && lane < NZ) s_du[lane - NX] = qvj;
+            NWT_SYNC();
+            if (lane == 0) {
+                double rhs[NU];
+                for (int r_ = 0; r_ < NU; ++r_) rhs[r_] = s_du[r_];
+                chol_solve<NU>(s_L, rhs);
+                for (int r_ = 0; r_ < NU; ++r_) { s_kf[r_] = -rhs[r_]; a.kf[(ib + k) * NU + r_] = -rhs[r_]; }
+            }
+            NWT_SYNC();
             // V = Qxx + Qxu K (symmetrised), v = qx + Qxu kf
-            for (int i = tid; i < NX * NX; i += nt) {
-                const int r_ = i / NX, c = i % NX;
-                double acc = 0.5 * (s_Q[r_ * NZ + c] + s_Q[c * NZ + r_]);
-                double a1 = 0.0, a2 = 0.0;
-                for (int e2 = 0; e2 < NU; ++e2) {
-                    a1 += 0.5 * (s_Q[r_ * NZ + NX + e2] + s_Q[(NX + e2) * NZ + r_]) * s_K[e2 * NX + c];
-                    a2 += 0.5 * (s_Q[c * NZ + NX + e2] + s_Q[(NX + e2) * NZ + c]) * s_K[e2 * NX + r_];
+            if (isX) {
+                const int c = jx;
+                double vnew[NX];
+                NWT_UNROLL for (int r_ = 0; r_ < NX; ++r_) {
+                    const double acc = 0.5 * (s_Q[r_ * NZS + c] + s_Q[c * NZS + r_]);
+                    double a1 = 0.0, a2 = 0.0;
+                    NWT_UNROLL for (int e2 = 0; e2 < NU; ++e2) {
+                        a1 += 0.5 * (s_Q[r_ * NZS + NX + e2] + s_Q[(NX + e2) * NZS + r_]) * s_K[e2 * NXS + c];
+                        a2 += 0.5 * (s_Q[c * NZS + NX + e2] + s_Q[(NX + e2) * NZS + c]) * s_K[e2 * NXS + r_];
+                    }
+                    vnew[r_] = acc + 0.5 * (a1 + a2);
                 }
-                s_V[i] = acc + 0.5 * (a1 + a2);
+                double acc = qvj;
+                NWT_UNROLL for (int e2 = 0; e2 < NU; ++e2) acc += 0.5 * (s_Q[c * NZS + NX + e2] + s_Q[(NX + e2) * NZS + c]) * s_kf[e2];
+                // (every read of the old V of this stage -- T and vt -- lies before the barriers above)
+                NWT_UNROLL for (int r_ = 0; r_ < NX; ++r_) { s_V[r_ * NXS + c] = vnew[r_]; Vs[(size_t)k * NX * NX + r_ * NX + c] = vnew[r_]; }
+                s_v[c] = acc;
+                vs[(size_t)k * NX + c] = acc;
             }
-            for (int i = tid; i < NX; i += nt) {
-                double acc = s_qv[i];
-                for (int e2 = 0; e2 < NU; ++e2) acc += 0.5 * (s_Q[i * NZ + NX + e2] + s_Q[(NX + e2) * NZ + i]) * s_kf[e2];
-                s_v[i] = acc;
-            }
-            for (int i = tid; i < NU * NX; i += nt) a.Kf[(ib + k) * NU * NX + i] = s_K[i];
-            for (int i = tid; i < NU; i += nt) a.kf[(ib + k) * NU + i] = s_kf[i];
-            __syncthreads();
-            for (int i = tid; i < NX * NX; i += nt) Vs[(size_t)k * NX * NX + i] = s_V[i];
-            for (int i = tid; i < NX; i += nt) vs[(size_t)k * NX + i] = s_v[i];
+            NWT_SYNC();
         }
-        __syncthreads();
+        NWT_SYNC();
         if (!s_flag) break;
         // wrong inertia: next delta
         if (attempt == 0) delta = (dlast == 0.0) ? 1e-4 : fmax(1e-20, dlast / 3.0);
         else delta *= (dlast == 0.0) ? 100.0 : 8.0;
         ++attempt;
         if (delta > 1e40) {
-            if (tid == 0) a.status[b] = ST_NUMERIC;
-            for (int i = tid; i < NU; i += nt) U[(size_t)N * NU + i] = U[(size_t)(N - 1) * NU + i];   // CPDP.py:191 holds whatever the solver returned
+            if (lane == 0) a.status[b] = ST_NUMERIC;
+            for (int i = lane; i < NU; i += nt) U[(size_t)N * NU + i] = U[(size_t)(N - 1) * NU + i];   // CPDP.py:191 holds whatever the solver returned
             return;
         }
-        __syncthreads();
+        NWT_SYNC();
     }
-    if (tid == 0 && delta > 0.0) a.dlast[b] = delta;
+    if (lane == 0 && delta > 0.0) a.dlast[b] = delta;
+#ifdef __CUDACC__
+    __threadfence_block();
+#endif
+    NWT_SYNC();
 
-    // ---- forward pass: step (dX, dU) and new multipliers
-    for (int i = tid; i < NX; i += nt) dX[i] = dfc[i];
-    __syncthreads();
+    // ---- forward pass: step (dX, dU) and new multipliers (lane i < NX: row i)
+    if (isX) { s_dx[jx] = dfc[jx]; dX[jx] = dfc[jx]; }
+    NWT_SYNC();
     for (int k = 0; k < N; ++k) {
         const double* Kk = a.Kf + (ib + k) * NU * NX;
         const double* kfk = a.kf + (ib + k) * NU;
-        const double* dxk = dX + (size_t)k * NX;
-        for (int i = tid; i < NU; i += nt) {
-            double acc = kfk[i];
-            for (int c = 0; c < NX; ++c) acc += Kk[i * NX + c] * dxk[c];
-            dU[(size_t)k * NU + i] = acc;
-        }
-        for (int i = tid; i < NX; i += nt) {
-            double acc = vs[(size_t)k * NX + i];
-            for (int c = 0; c < NX; ++c) acc += Vs[(size_t)k * NX * NX + i * NX + c] * dxk[c];
-            lamn[(size_t)k * NX + i] = acc;
-        }
-        __syncthreads();
         const double* ABg = a.AB + (ib + k) * NX * NZ;
-        const double* duk = dU + (size_t)k * NU;
-        for (int i = tid; i < NX; i += nt) {
-            double acc = dfc[(size_t)(k + 1) * NX + i];
-            for (int c = 0; c < NX; ++c) acc += ABg[i * NZ + c] * dxk[c];
-            for (int c = 0; c < NU; ++c) acc += ABg[i * NZ + NX + c] * duk[c];
-            dX[(size_t)(k + 1) * NX + i] = acc;
+        // rows of K, V, [A B] for this lane: one batch of independent loads
+        double kr[NX], vr[NX], ar[NZ];
+        const int lu = (lane < NU) ? lane : 0;
+        NWT_UNROLL for (int c = 0; c < NX; ++c) { kr[c] = Kk[lu * NX + c]; vr[c] = Vs[(size_t)k * NX * NX + jx * NX + c]; }
+        NWT_UNROLL for (int c = 0; c < NZ; ++c) ar[c] = ABg[jx * NZ + c];
+        const double kf0 = kfk[lu], vs0 = vs[(size_t)k * NX + jx], df0 = dfc[(size_t)(k + 1) * NX + jx];
+        if (lane < NU) {
+            double acc = kf0;
+            NWT_UNROLL for (int c = 0; c < NX; ++c) acc += kr[c] * s_dx[c];
+            s_du[lane] = acc;
+            dU[(size_t)k * NU + lane] = acc;
         }
-        __syncthreads();
+        if (isX) {
+            double acc = vs0;
+            NWT_UNROLL for (int c = 0; c < NX; ++c) acc += vr[c] * s_dx[c];
+            lamn[(size_t)k * NX + jx] = acc;
+        }
+        NWT_SYNC();
+        double nx = 0.0;
+        if (isX) {
+            double acc = df0;
+            NWT_UNROLL for (int c = 0; c < NX; ++c) acc += ar[c] * s_dx[c];
+            NWT_UNROLL for (int c = 0; c < NU; ++c) acc += ar[NX + c] * s_du[c];
+            nx = acc;
+        }
+        NWT_SYNC();
+        if (isX) { s_dx[jx] = nx; dX[(size_t)(k + 1) * NX + jx] = nx; }
+        NWT_SYNC();
     }
-    for (int i = tid; i < NX; i += nt) {
-        double acc = vs[(size_t)N * NX + i];
-        for (int c = 0; c < NX; ++c) acc += Vs[(size_t)N * NX * NX + i * NX + c] * dX[(size_t)N * NX + c];
-        lamn[(size_t)N * NX + i] = acc;
+    if (isX) {
+        double acc = vs[(size_t)N * NX + jx];
+        NWT_UNROLL for (int c = 0; c < NX; ++c) acc += Vs[(size_t)N * NX * NX + jx * NX + c] * s_dx[c];
+        lamn[(size_t)N * NX + jx] = acc;
     }
-    __syncthreads();
+#ifdef __CUDACC__
+    __threadfence_block();
+#endif
+    NWT_SYNC();
 
     // ---- directional derivative of the objective along the step
     double gd = 0.0, bad = 0.0;
-    for (int i = tid; i < (N + 1) * NX; i += nt) if (!(fabs(lamn[i]) < 1e300)) bad = 1.0;
-    for (int k = tid; k < N; k += nt) {
+    for (int i = lane; i < (N + 1) * NX; i += nt) if (!(fabs(lamn[i]) < 1e300)) bad = 1.0;
+    for (int k = lane; k < N; k += nt) {
         const double* g = a.gq + (ib + k) * NZ;
         for (int i = 0; i < NX; ++i) gd += g[i] * dX[(size_t)k * NX + i];
         for (int i = 0; i < NU; ++i) gd += g[NX + i] * dU[(size_t)k * NU + i];
     }
-    for (int i = tid; i < NX; i += nt) gd += s_hx[i] * dX[(size_t)N * NX + i];
-    bad = block_reduce(bad, red, true);
-    gd = block_reduce(gd, red, false);
+    for (int i = lane; i < NX; i += nt) gd += s_hx[i] * dX[(size_t)N * NX + i];
+    bad = nwt_reduce(bad, red, true);
+    gd = nwt_reduce(gd, red, false);
     if (bad != 0.0 || !(gd == gd)) {
-        if (tid == 0) a.status[b] = ST_NUMERIC;
-        for (int i = tid; i < NU; i += nt) U[(size_t)N * NU + i] = U[(size_t)(N - 1) * NU + i];
+        if (lane == 0) a.status[b] = ST_NUMERIC;
+        for (int i = lane; i < NU; i += nt) U[(size_t)N * NU + i] = U[(size_t)(N - 1) * NU + i];
         return;
     }
 
     // ---- IPOPT filter line search (Waechter & Biegler 2006, Sec. 2.3; phi = J, theta = |g|_1, default constants
     //      gamma_theta 1e-5, gamma_phi 1e-8, delta 1, s_theta 1.1, s_phi 2.3, eta_phi 1e-8; no second-order
-    //      correction, no restoration phase).  One thread per interval re-integrates the RK4 map at each trial point.
+    //      correction, no restoration phase).  One lane per interval re-integrates the RK4 map at each trial point.
     const double th0 = g1;
-    if (it == 0 && tid == 0) a.th_init[b] = fmax(1.0, th0);
-    __syncthreads();
+    if (it == 0 && lane == 0) a.th_init[b] = fmax(1.0, th0);
+#ifdef __CUDACC__
+    __threadfence_block();
+#endif
+    NWT_SYNC();
     const double theta_min = 1e-4 * a.th_init[b], theta_max = 1e4 * a.th_init[b];
     const int nf = a.nfilt[b];
     const double* filt = a.filt + (size_t)b * FILTER_CAP * 2;
@@ -618,7 +692,7 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
     bool ok = false, ftype = false;
     for (int ls = 0; ls <= 30; ++ls) {
         double Jt = 0.0, gt = 0.0;
-        for (int k = tid; k <= N; k += nt) {
+        for (int k = lane; k <= N; k += nt) {
             double xk[NX];
             PdBuf pdb;
             const double* pd = pd_at(pd0, grid_time(a.T, N, k), pdb);
@@ -637,10 +711,10 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
             }
             if (k == 0) for (int i = 0; i < NX; ++i) gt += fabs(a.x0[(size_t)b * NX + i] - xk[i]);
         }
-        Jt = block_reduce(Jt, red, false);
-        gt = block_reduce(gt, red, false);
+        Jt = nwt_reduce(Jt, red, false);
+        gt = nwt_reduce(gt, red, false);
         bool acc = (Jt == Jt) && (gt == gt) && fabs(Jt) < 1e300 && gt <= theta_max;
-        for (int e = 0; acc && e < nf; ++e) if (gt >= filt[2 * e] && Jt >= filt[2 * e + 1]) acc = false;
+        for (int e2 = 0; acc && e2 < nf; ++e2) if (gt >= filt[2 * e2] && Jt >= filt[2 * e2 + 1]) acc = false;
         if (acc) {
             const bool switching = (gd < 0) && (alpha * sw_lhs > sw_rhs);
             if (switching && th0 <= theta_min) {
@@ -654,36 +728,35 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
         alpha *= 0.5;
     }
     if (!ok) {
-        if (tid == 0) a.status[b] = ST_LINESEARCH;
-        for (int i = tid; i < NU; i += nt) U[(size_t)N * NU + i] = U[(size_t)(N - 1) * NU + i];
+        if (lane == 0) a.status[b] = ST_LINESEARCH;
+        for (int i = lane; i < NU; i += nt) U[(size_t)N * NU + i] = U[(size_t)(N - 1) * NU + i];
         return;
     }
-    if (!ftype && tid == 0 && nf < FILTER_CAP) {
+    if (!ftype && lane == 0 && nf < FILTER_CAP) {
         a.filt[((size_t)b * FILTER_CAP + nf) * 2] = (1 - 1e-5) * th0;
         a.filt[((size_t)b * FILTER_CAP + nf) * 2 + 1] = J0 - 1e-8 * th0;
         a.nfilt[b] = nf + 1;
     }
 
     // ---- update
-    for (int i = tid; i < (N + 1) * NX; i += nt) {
+    for (int i = lane; i < (N + 1) * NX; i += nt) {
         X[i] += alpha * dX[i];
         Lam[i] += alpha * (lamn[i] - Lam[i]);
     }
-    for (int i = tid; i < N * NU; i += nt) U[i] += alpha * dU[i];
-    if (tid == 0) a.iters[b] = it + 1;
+    for (int i = lane; i < N * NU; i += nt) U[i] += alpha * dU[i];
+    if (lane == 0) a.iters[b] = it + 1;
 }
 
-// One 64-thread CTA per problem walks the N stages serially (block LDL' of the KKT matrix, then the line search): latency
-// bound, so residency beats registers -- measured on the 4096-OCP batch: 1 -> 58.6 ms per solve, 8 -> 53.3, 16 -> 50.6
-// (64 registers, ~600 B of spills per thread).
+// One warp per problem walks the N stages serially (block LDL' of the KKT matrix, then the line search); a persistent grid
+// strides over the compacted list of problems still iterating.
 #ifndef CPDP_NEWTON_MINB
-#define CPDP_NEWTON_MINB 16
+#define CPDP_NEWTON_MINB 8
 #endif
 CPDP_GLOBAL void __launch_bounds__(NEWTON_THREADS, CPDP_NEWTON_MINB) k_newton_step(SolveArgs a) {
     const int nact = *a.nact;
     for (int pi = blockIdx.x; pi < nact; pi += gridDim.x) {
         newton_step_problem(a, a.act[pi]);
-        __syncthreads();
+        NWT_SYNC();
     }
 }
 

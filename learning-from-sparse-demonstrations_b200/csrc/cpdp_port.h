@@ -33,6 +33,7 @@
 #define CPDP_SHARED static
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 struct cpdp_emu_dim3 { int x, y, z; };
 extern thread_local cpdp_emu_dim3 threadIdx;
 extern cpdp_emu_dim3 blockIdx, blockDim, gridDim;
