@@ -196,16 +196,19 @@ def flop_model(info, n, m, r, N, S, iters_sum, B, cnt, mode):
         + 4 * (nt + n * r)
     ny_r, ny_f = nt + n * r, n * r
     if mode == "bdf":
-        # k_riccati_bdf as built: one real Schur form per Jacobian, Bartels-Stewart solves.
-        # per rhs evaluation (= Newton iteration): Riccati rhs, two-sided real transforms (2 n^3 + 2 nt n each way), block
-        #   rotations, the complex triangular Lyapunov sweep (8 flops per complex multiply-add), W block, norms/updates;
+        # k_riccati_bdf as built in round 2: full n x (n+r) state columns, dense products in the Newton solve.
+        # per rhs evaluation (= Newton iteration): right-hand side on the 20 columns of [P|W] (sparse fx, fu through COO lists,
+        #   Huu^-1, the Y'Yp term), four 13^3 real products of the two-sided Schur transforms, the two block-rotation stencils,
+        #   the complex triangular Lyapunov sweep (8 flops per complex multiply-add), the W block (X C and (I+cL)^-1), norms;
         # per accepted step: PMP matrices at t_new, predictor / psi / difference update, change_D;
-        # per "LU" event (new c): (I + cT)^-1 by back substitution, pivots, rotation, two n^3 products;
-        # per Jacobian: closed-form L, C, Givens-Hessenberg + Francis QR with vectors (~25 n^3 + 10/3 n^3, LAPACK count)
+        # per "LU" event (new c): Gauss-Jordan inverse of I + cL on [A | I] (26 columns, 13 pivots), Lyapunov pivots;
+        # per Jacobian: closed-form L, C; Householder-Hessenberg + Francis QR with vectors (~25 n^3 + 10/3 n^3, LAPACK count)
+        ncol = n + r
+        rhs_cols = ncol * (2 * nnzu + 2 * m * m + 2 * nnzx + 2 * m * n + 6 * n)
         sweep_macs = sum((n - 1 - i) + (n - 1 - j) for i in range(n) for j in range(i, n))
-        solve_bs = 2 * (2 * n ** 3 + 2 * nt * n) + 2 * 16 * nt + 8 * sweep_macs + 10 * nt + 4 * n * n * r
-        back = cnt[0] * (ric + solve_bs + 8 * ny_r) \
-            + cnt[1] * (pmp + 30 * ny_r) + cnt[4] * (4.0 / 3 * n ** 3 + 10 * nt + 16 * n * n + 4 * n ** 3) \
+        solve_bs = 4 * 2 * n ** 3 + 24 * nt + 20 * n * n + 8 * sweep_macs + 12 * nt + 2 * (2 * n * n * r) + 4 * n * n
+        back = cnt[0] * (rhs_cols + solve_bs + 8 * n * ncol) \
+            + cnt[1] * (pmp + 30 * n * ncol) + cnt[4] * (2 * n * n * 2 * n + 12 * nt) \
             + cnt[5] * (2 * n * n * m * 2 + 2 * n ** 3 + 2 * n * n * r + 25 * n ** 3 + 10.0 / 3 * n ** 3)
     else:
         back = cnt[0] * (ric + pmp * 6.0 / 7 + 16 * ny_r)

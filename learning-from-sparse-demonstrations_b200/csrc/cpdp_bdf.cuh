@@ -105,10 +105,10 @@ constexpr int XB = XA + NX * NCS;
 constexpr int GHM = XB + NX * NCS;               // fu Huu^{-1}, [NX][NU]
 constexpr int YPM = GHM + NX * NU;               // Huu^{-1} Y, [NU][NX]
 constexpr int ROT = YPM + NU * NX;               // block rotations G: ga | gbr | gbi | partner   (4 x NX)
-constexpr int RU = ROT + 4 * NX;                 // change_D: RU | R | U, 6 x 6 each (also Householder vector scratch)
-constexpr int FLAG = RU + 108;                   // 2 ints
+constexpr int RU = (ROT + 4 * NX + 1) & ~1;                 // change_D: RU | R | U, 6 x 6 each (also Householder vector scratch, sweep store dump: 128)
+constexpr int FLAG = RU + 128;                   // 2 ints
 constexpr int END = FLAG + 2;
-static_assert(Y2 % 2 == 0 && T2S % 2 == 0 && TD % 2 == 0 && PV % 2 == 0, "complex arrays are read with 128-bit loads");
+static_assert(Y2 % 2 == 0 && T2S % 2 == 0 && TD % 2 == 0 && PV % 2 == 0 && RU % 2 == 0, "complex arrays are read with 128-bit loads");
 }  // namespace bo
 constexpr int BDF_SMEM_DOUBLES = bo::END;
 constexpr size_t BDF_SMEM_BYTES = (size_t)BDF_SMEM_DOUBLES * sizeof(double);
@@ -761,11 +761,15 @@ CPDP_D void bdf_sweep(double* sm, const double c) {
             ai = (red[32 + tid] + red[32 + tid + 1]) + (red[32 + tid + 2] + red[32 + tid + 3]);
         }
 #endif
-        if (valid && sub == 0) {
+        {   // branch-free: every lane forms the entry; lanes without one (and the mirror of a diagonal entry) store to a scratch slot
             const double rr = cv.x - c * ar, ri = cv.y - c * ai;
             const double yr = rr * pv.x - ri * pv.y, yi = rr * pv.y + ri * pv.x;
-            BDF_ST2(Y + 2 * (i * n + j), yr, (i == j) ? 0.0 : yi);
-            if (i != j) BDF_ST2(Y + 2 * (j * n + i), yr, -yi);
+            const bool st = valid && (sub == 0);
+            double* dump = sm + bo::RU + 2 * tid;                 // (change_D's scratch: free during a Newton solve)
+            double* p1 = st ? Y + 2 * (i * n + j) : dump;
+            double* p2 = (st && i != j) ? Y + 2 * (j * n + i) : dump + 64;
+            BDF_ST2(p1, yr, (i == j) ? 0.0 : yi);
+            BDF_ST2(p2, yr, -yi);
         }
         // next anti-diagonal: d > n-1: the first row of the diagonal drops by one (i - 1, same j); else the column does
         if (d > n - 1) --i; else --j;
