@@ -214,9 +214,12 @@ constexpr int KPC = HESS_THREADS / NZ;          // intervals per CTA
 #ifndef CPDP_HESS_MINB
 #define CPDP_HESS_MINB 1
 #endif
+#ifndef CPDP_HESS_ACC_UNROLL
+#define CPDP_HESS_ACC_UNROLL NZ         // (partial unrolling sends hz / Hc to local memory: dynamic indices)
+#endif
 CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian(SolveArgs a) {
-    CPDP_SHARED double s_x[KPC][NX];
-    CPDP_SHARED double s_mu[KPC][NX];
+    CPDP_SHARED double s_x[2][KPC][NX];        // double-buffered: the next stage's states / adjoints are fetched while this one computes
+    CPDP_SHARED double s_mu[2][KPC][NX];
     CPDP_SHARED double s_u[KPC][NU];
     CPDP_SHARED double s_th[KPC][NP];
     CPDP_SHARED double s_pd[KPC][NQT > 0 ? NQT : 1];
@@ -259,29 +262,49 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
         for (int i = 0; i < NU; ++i) du[i] = (NX + i == j) ? 1.0 : 0.0;
         for (int i = 0; i < NZ; ++i) Hc[i] = 0.0;
 
+        // stage states + adjoints of every interval of this group: fetched one stage ahead into registers, parked in the other
+        // shared-memory buffer after the Hessian accumulation (the global-load latency hides behind the model code)
+        constexpr int NPRE = (KPC * 2 * NX + HESS_THREADS - 1) / HESS_THREADS;
+        double pre[NPRE];
+        const int nstage = 4 * a.S;
+#define HESS_FETCH(sidx)                                                                                        \
+        for (int p_ = 0; p_ < NPRE; ++p_) {                                                                     \
+            const int t = tid + p_ * HESS_THREADS;                                                              \
+            pre[p_] = 0.0;                                                                                      \
+            if (t < KPC * 2 * NX) {                                                                             \
+                const int q = t / (2 * NX), e = t % (2 * NX);                                                   \
+                const int g2 = s_gi[q];                                                                         \
+                if (g2 >= 0) {                                                                                  \
+                    const size_t base = ((size_t)g2 * nstage + (size_t)(sidx)) * NX;                            \
+                    pre[p_] = (e < NX) ? a.xs[base + e] : a.mu[base + e - NX];                                  \
+                }                                                                                               \
+            }                                                                                                   \
+        }
+#define HESS_STASH(buf)                                                                                         \
+        for (int p_ = 0; p_ < NPRE; ++p_) {                                                                     \
+            const int t = tid + p_ * HESS_THREADS;                                                              \
+            if (t < KPC * 2 * NX) {                                                                             \
+                const int q = t / (2 * NX), e = t % (2 * NX);                                                   \
+                if (e < NX) s_x[buf][q][e] = pre[p_]; else s_mu[buf][q][e - NX] = pre[p_];                      \
+            }                                                                                                   \
+        }
+        HESS_FETCH(0)
+        HESS_STASH(0)
+        __syncthreads();
         for (int s = 0; s < a.S; ++s) {
             for (int i = 0; i < NX; ++i) Sn[i] = Sx[i];
             for (int st = 0; st < 4; ++st) {
-                // stage state + adjoint for every interval of this group
-                for (int t = tid; t < KPC * 2 * NX; t += HESS_THREADS) {
-                    const int q = t / (2 * NX), e = t % (2 * NX);
-                    const int g2 = s_gi[q];
-                    if (g2 >= 0) {
-                        const size_t base = ((size_t)g2 * 4 * a.S + (size_t)s * 4 + st) * NX;
-                        if (e < NX) s_x[q][e] = a.xs[base + e];
-                        else s_mu[q][e - NX] = a.mu[base + e - NX];
-                    }
-                }
-                __syncthreads();
+                const int sidx = s * 4 + st, cur = sidx & 1;
+                if (sidx + 1 < nstage) { HESS_FETCH(sidx + 1) }
                 if (mine) {
                     const double ca = aco[st] * DT;
                     for (int i = 0; i < NX; ++i) dX[i] = Sx[i] + ca * df[i];
-                    Model::dir(s_x[kk], s_u[kk], s_th[kk], s_pd[kk], s_mu[kk], bco[st] * DT, dX, du, df, hz);
+                    Model::dir(s_x[cur][kk], s_u[kk], s_th[kk], s_pd[kk], s_mu[cur][kk], bco[st] * DT, dX, du, df, hz);
                     for (int i = 0; i < NX; ++i) s_S[kk][j][i] = dX[i];
                 }
                 __syncthreads();
                 if (mine) {
-                    for (int i = 0; i < NZ; ++i) {
+                    CPDP_PRAGMA_UNROLL(CPDP_HESS_ACC_UNROLL) for (int i = 0; i < NZ; ++i) {
                         double acc = (i >= NX) ? hz[i] : 0.0;
                         const double* col = s_S[kk][i];
 #ifdef __CUDACC__
@@ -300,9 +323,13 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
                     const double cb = bco[st] * DT;
                     for (int i = 0; i < NX; ++i) Sn[i] += cb * df[i];
                 }
+                if (sidx + 1 < nstage) { HESS_STASH(cur ^ 1) }     // (the other buffer was last read by the previous stage's model code)
+                __syncthreads();
             }
             for (int i = 0; i < NX; ++i) Sx[i] = Sn[i];
         }
+#undef HESS_FETCH
+#undef HESS_STASH
         if (mine) {
             double* AB = a.AB + (size_t)gi * NX * NZ;
             for (int i = 0; i < NX; ++i) AB[i * NZ + j] = Sx[i];

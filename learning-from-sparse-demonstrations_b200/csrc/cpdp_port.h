@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 // keeps a loop rolled: the B200 instruction caches are 6 KB (L0) / 32 KB (L1.5) per SM, and the sweeps are fetch-bound
 #define CPDP_LOOP _Pragma("unroll 1")
+#define CPDP_PRAGMA_STR(x) _Pragma(#x)
+#define CPDP_PRAGMA_UNROLL(n) CPDP_PRAGMA_STR(unroll n)
 #define CPDP_HD __host__ __device__ __forceinline__
 #define CPDP_D __device__ __forceinline__
 #define CPDP_D_NOINLINE __device__ __noinline__
@@ -26,6 +28,7 @@
 #include <cstring>
 #include <algorithm>
 #define CPDP_LOOP
+#define CPDP_PRAGMA_UNROLL(n)
 #define CPDP_HD inline
 #define CPDP_D inline
 #define CPDP_D_NOINLINE inline
