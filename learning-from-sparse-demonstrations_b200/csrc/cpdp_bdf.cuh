@@ -180,7 +180,9 @@ CPDP_D_NOINLINE void bdf_lmul_to(const double* __restrict__ AT, const int as, co
         const double xk = x[k * xs];
         BDF_UNROLL for (int i = 0; i < NH; ++i) out[i] += A0[k * as + i] * xk;
     }
-    BDF_UNROLL for (int i = 0; i < NH; ++i) dst[(i0 + i) * ds] = out[i];
+    // (for odd NX the two halves overlap in one row: the second half leaves it to the first)
+    const int first = (i0 > 0) ? 2 * NH - NX : 0;
+    BDF_UNROLL for (int i = 0; i < NH; ++i) if (i >= first) dst[(i0 + i) * ds] = out[i];
 }
 // lane -> (column, first row) of the two-halves mapping; false for idle lanes
 CPDP_D bool bdf_half(const int lane, int& col, int& i0) {

@@ -558,7 +558,7 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
             // T[:, j] = V [A B][:, j]   (V symmetric: V[e][i] = V[i][e] is its own contraction-major operand)
             double t[NX];
             NWT_UNROLL for (int i = 0; i < NX; ++i) t[i] = 0.0;
-            nwt_mac<NX>(s_V, NXS, s_AB + jz, NZS, NX, t);
+            if (isZ) nwt_mac<NX>(s_V, NXS, s_AB + jz, NZS, NX, t);
             // gq[j] = gL[j] - [A B][:, j]' lam_{k+1};  qv[j] = gq[j] + [A B][:, j]' vt
             double gqj = gl;
             NWT_UNROLL for (int e2 = 0; e2 < NX; ++e2) gqj -= ab[e2] * s_lk[e2];
@@ -568,7 +568,7 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
             // Q[:, j] = sym(H)[:, j] + delta e_j + [A B]' T[:, j]
             double q[NZ];
             NWT_UNROLL for (int r_ = 0; r_ < NZ; ++r_) q[r_] = hq[r_] + ((isZ && r_ == jz) ? delta : 0.0);
-            nwt_mac<NZ>(s_AB, NZS, s_T + jz, NZS, NX, q);          // (reads my own column of T: no barrier needed)
+            if (isZ) nwt_mac<NZ>(s_AB, NZS, s_T + jz, NZS, NX, q);          // (reads my own column of T: no barrier needed)
             if (isZ) { NWT_UNROLL for (int r_ = 0; r_ < NZ; ++r_) s_Q[r_ * NZS + jz] = q[r_]; }
             NWT_SYNC();
             // Quu = L L'
