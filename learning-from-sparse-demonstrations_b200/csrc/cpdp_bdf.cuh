@@ -107,7 +107,12 @@ constexpr int YPM = GHM + NX * NU;               // Huu^{-1} Y, [NU][NX]
 constexpr int ROT = YPM + NU * NX;               // block rotations G: ga | gbr | gbi | partner   (4 x NX)
 constexpr int RU = (ROT + 4 * NX + 1) & ~1;                 // change_D: RU | R | U, 6 x 6 each (also Householder vector scratch, sweep store dump: 128)
 constexpr int FLAG = RU + 128;                   // 2 ints
+#ifdef CPDP_BDF_TIMING
+constexpr int TS = FLAG + 2;                     // developer timing build: Schur sub-phase clocks (8)
+constexpr int END = TS + 8;
+#else
 constexpr int END = FLAG + 2;
+#endif
 static_assert(Y2 % 2 == 0 && T2S % 2 == 0 && TD % 2 == 0 && PV % 2 == 0 && RU % 2 == 0, "complex arrays are read with 128-bit loads");
 }  // namespace bo
 constexpr int BDF_SMEM_DOUBLES = bo::END;
@@ -159,11 +164,15 @@ CPDP_D double bdf_rcp(double x) {
 #define BDF_TB(ph, var, expr) do { const long long t0__ = clock64(); var = (expr); tp[ph] += clock64() - t0__; } while (0)
 #define BDF_TP_PARAM , long long* tp
 #define BDF_TP_ARG , tp
+#define BDF_TS0() const long long ts0__ = clock64()
+#define BDF_TS(i) do { if (threadIdx.x == 0) sm[bo::TS + (i)] += (double)(clock64() - ts0__); } while (0)
 #else
 #define BDF_T(ph, ...) do { __VA_ARGS__; } while (0)
 #define BDF_TB(ph, var, expr) do { var = (expr); } while (0)
 #define BDF_TP_PARAM
 #define BDF_TP_ARG
+#define BDF_TS0()
+#define BDF_TS(i)
 #endif
 
 // THE product of the hot loop, one out-of-line instance:  dst[(i0 + i) * ds] = sum_k AT[k][i0 + i] x[k * xs],  i < NH.
@@ -171,18 +180,29 @@ CPDP_D double bdf_rcp(double x) {
 // (stride 1) of an exchange buffer.  Two lanes share one output column (rows [0, NH) and [NX - NH, NX)), so a 13 x 13 product
 // occupies 26 lanes with 7 independent accumulator chains each; k is fully unrolled (every load in flight at once) --
 // affordable because this is the only copy.  Summation order: ascending k.
-CPDP_D_NOINLINE void bdf_lmul_to(const double* __restrict__ AT, const int as, const double* __restrict__ x, const int xs,
-                                 double* __restrict__ dst, const int ds, const int i0) {
+template <int AS>
+CPDP_D_NOINLINE void bdf_lmul_t(const double* __restrict__ AT, const double* __restrict__ x, const int xs,
+                                double* __restrict__ dst, const int ds, const int i0) {
     double out[NH];
     BDF_UNROLL for (int i = 0; i < NH; ++i) out[i] = 0.0;
     const double* A0 = AT + i0;
     BDF_PRAGMA_UNROLL(CPDP_BDF_LMUL_UNROLL) for (int k = 0; k < NX; ++k) {
         const double xk = x[k * xs];
-        BDF_UNROLL for (int i = 0; i < NH; ++i) out[i] += A0[k * as + i] * xk;
+        if constexpr (AS % 2 == 0 && (NX - NH) % 2 == 0) {           // rows of A start 16-byte aligned in both halves
+            double a[NH + 1];
+            BDF_UNROLL for (int i = 0; i + 1 < NH + 1; i += 2) { const auto v = BDF_LD2(A0 + k * AS + i); a[i] = v.x; a[i + 1] = v.y; }
+            BDF_UNROLL for (int i = 0; i < NH; ++i) out[i] += a[i] * xk;
+        } else {
+            BDF_UNROLL for (int i = 0; i < NH; ++i) out[i] += A0[k * AS + i] * xk;
+        }
     }
     // (for odd NX the two halves overlap in one row: the second half leaves it to the first)
     const int first = (i0 > 0) ? 2 * NH - NX : 0;
     BDF_UNROLL for (int i = 0; i < NH; ++i) if (i >= first) dst[(i0 + i) * ds] = out[i];
+}
+CPDP_D void bdf_lmul_to(const double* AT, const int as, const double* x, const int xs, double* dst, const int ds, const int i0) {
+    if (as == QS) bdf_lmul_t<QS>(AT, x, xs, dst, ds, i0);        // (as is a literal at every call site: one branch survives)
+    else bdf_lmul_t<NCS>(AT, x, xs, dst, ds, i0);
 }
 // lane -> (column, first row) of the two-halves mapping; false for idle lanes
 CPDP_D bool bdf_half(const int lane, int& col, int& i0) {
@@ -410,7 +430,16 @@ CPDP_D double bdf_rsqrt(double x) {
 //   Hessenberg form by Householder reflections (column-owned left application, row-owned right application);
 //   Francis double-shift QR (EISPACK hqr2 control flow) with the deflation / start-row scans done by all lanes in parallel
 //   (one vote each) and reflectors from one rsqrt + one reciprocal; two warp barriers per bulge step.
+#ifdef CPDP_SCHUR_STATS
+#include <cstdio>
+struct SchurStats { long long calls = 0, sweeps = 0, steps = 0, exc = 0, maxits = 0; ~SchurStats() { fprintf(stderr, "SCHUR calls %lld sweeps %lld steps %lld exceptional %lld max its %lld\n", calls, sweeps, steps, exc, maxits); } };
+static SchurStats g_ss;
+#define SS(...) do { if (threadIdx.x == 0) { __VA_ARGS__; } } while (0)
+#else
+#define SS(...)
+#endif
 CPDP_D bool schur_real_w0(double* sm, double* H, double* Z, double* vb) {
+    SS(g_ss.calls++);
     constexpr int n = NX;
     const int lane = threadIdx.x;
     const double EPS = 2.220446049250313e-16;
@@ -418,6 +447,7 @@ CPDP_D bool schur_real_w0(double* sm, double* H, double* Z, double* vb) {
     for (int i = lane; i < n * n; i += 32) Z[i] = (i / n == i % n) ? 1.0 : 0.0;
     BDF_SYNC();
     // ---- Hessenberg form
+    { BDF_TS0();
     CPDP_LOOP for (int j = 0; j < n - 2; ++j) {
         double sig = 0.0;
         BDF_UNROLL for (int i = 0; i < n; ++i) { const double v = h_(i, j); sig += (i >= j + 2) ? v * v : 0.0; }
@@ -455,6 +485,7 @@ CPDP_D bool schur_real_w0(double* sm, double* H, double* Z, double* vb) {
         }
         BDF_SYNC();
     }
+    BDF_TS(0); }
     double norm = 0.0;
     if (lane < n) { BDF_UNROLL for (int jj = 0; jj < n; ++jj) norm += (jj + 1 >= lane) ? fabs(h_(lane, jj)) : 0.0; }
     norm = bdf_reduce(norm, false);
@@ -463,6 +494,7 @@ CPDP_D bool schur_real_w0(double* sm, double* H, double* Z, double* vb) {
     while (en >= 0) {
         int its = 0;
         while (true) {
+            BDF_TS0();
             int l = 0;
             {
                 bool small = false;
@@ -480,7 +512,9 @@ CPDP_D bool schur_real_w0(double* sm, double* H, double* Z, double* vb) {
             double x = h_(en, en), y = h_(en - 1, en - 1), w = h_(en, en - 1) * h_(en - 1, en);
             // exceptional shift every 14th sweep: blocks holding two nearly identical complex pairs (the x/y symmetry
             // of the quadrotor) converge only linearly under the standard shifts and can need > 100 sweeps
+            SS(g_ss.sweeps++; if (its + 1 > g_ss.maxits) g_ss.maxits = its + 1);
             if (its > 0 && its % 14 == 0) {
+                SS(g_ss.exc++);
                 const double s = fabs(h_(en, en - 1)) + fabs(h_(en - 1, en - 2));
                 x = y = 0.75 * s + h_(en, en);
                 w = -0.4375 * s * s;
@@ -511,8 +545,10 @@ CPDP_D bool schur_real_w0(double* sm, double* H, double* Z, double* vb) {
             }
             BDF_SYNC();
             if (lane == 0 && l >= 1) h_(l, l - 1) = 0.0;
+            BDF_TS(1);
             CPDP_LOOP for (int k = m; k <= en - 1; ++k) {
                 const bool notlast = (k != en - 1);
+                SS(g_ss.steps++);
                 if (k != m) { p = h_(k, k - 1); q = h_(k + 1, k - 1); r = notlast ? h_(k + 2, k - 1) : 0.0; }
                 const double sig = p * p + q * q + r * r;
                 if (sig == 0.0) continue;                             // (uniform)
@@ -548,6 +584,7 @@ CPDP_D bool schur_real_w0(double* sm, double* H, double* Z, double* vb) {
                 }
                 BDF_SYNC();
             }
+            BDF_TS(2);                                                   // (scans + bulge chase of this sweep)
         }
     }
 #undef h_
@@ -570,6 +607,7 @@ CPDP_D_NOINLINE bool bdf_schur() {
     BDF_SYNC();
     const bool ok = schur_real_w0(sm, Tr, Zm, sm + bo::RU);
     BDF_SYNC();
+    BDF_TS0();
     if (!ok && lane == 0) flag[1] = 0;
     // ---- one unitary rotation per 2 x 2 block:  G = [[c, s], [-conj(s), c]],  T <- G T G^H.  The Schur vectors stay REAL;
     //      the block-diagonal unitary factor is kept as per-index coefficients (Z = Q G^H):
@@ -615,6 +653,7 @@ CPDP_D_NOINLINE bool bdf_schur() {
         BDF_SYNC();
     }
     BDF_SYNC();
+    BDF_TS(3);
     // k-major product operands Q[k][i] (for Q' x) and QT[k][i] = Q[i][k] (for Q x); T packed for the sweep
     CPDP_LOOP for (int e = lane; e < n * n; e += BDF_THREADS) {
         const int r_ = e / n, c_ = e % n;
@@ -628,6 +667,7 @@ CPDP_D_NOINLINE bool bdf_schur() {
     }
     if (lane < n) BDF_ST2(sm + bo::TD + 2 * lane, Tr[lane * n + lane], Ti[lane * n + lane]);
     BDF_SYNC();
+    BDF_TS(4);                                                           // (rotations + packing)
     return flag[1] != 0;
 }
 
@@ -694,17 +734,12 @@ CPDP_D_NOINLINE bool bdf_factor(const double c) {
         BDF_SYNC();
         double ak[n];
         BDF_UNROLL for (int i = 0; i < n; ++i) ak[i] = XA[i * NCS + k];
-        double piv = 0.0;
-        BDF_UNROLL for (int i = 0; i < n; ++i) if (i == k) piv = ak[i];
-        const double ip = 1.0 / piv;
+        const double ip = bdf_rcp(XA[k * NCS + k]);              // (either sign; the argmax above made it the largest of its column)
         BDF_SYNC();
         if (own) {
-            double col[n];
-            BDF_UNROLL for (int i = 0; i < n; ++i) col[i] = mine[i * NCS];
-            double ck = 0.0;
-            BDF_UNROLL for (int i = 0; i < n; ++i) if (i == k) ck = col[i];
-            const double t = ck * ip;
-            BDF_UNROLL for (int i = 0; i < n; ++i) mine[i * NCS] = (i == k) ? t : col[i] - ak[i] * t;
+            const double t = mine[k * NCS] * ip;
+            BDF_UNROLL for (int i = 0; i < n; ++i) mine[i * NCS] -= ak[i] * t;
+            mine[k * NCS] = t;                                   // (row k itself: the scaled pivot row)
         }
         BDF_SYNC();
     }
@@ -726,17 +761,32 @@ CPDP_D void bdf_sweep(double* sm, const double c) {
     const int tid = threadIdx.x;
     const double* T2 = sm + bo::T2S; double* Y = sm + bo::Y2; const double* PVm = sm + bo::PV;
     const int e = tid >> 2, sub = tid & 3;
-    // The four operand addresses of a lane move by constant strides from one anti-diagonal to the next (two regimes: above the
-    // main anti-diagonal the row index of the entry drops, below it the column index does), so they are carried in registers and
-    // stepped -- no address arithmetic between the barrier and the loads.  Lanes without an entry run on entry (0, 0), unstored.
+    // Lanes without an entry on the current anti-diagonal run on whatever their (i, j) addresses (all inside the kernel's
+    // shared memory, see the asserts below) and store to a scratch slot, so the operand offsets of every lane move by
+    // constants from one anti-diagonal to the next (above the main anti-diagonal the row index of an entry drops, below it
+    // the column index does): they are carried in registers and stepped -- no address arithmetic behind the barrier.
+    static_assert(bo::Y2 - 2 * 7 * NX >= 0 && bo::T2S - 2 * 8 * TW >= 0, "sweep: idle-lane operands below the arrays");
+    static_assert(bo::Y2 + 2 * ((NX + 7 + 4 * SWQ) * NX + NX) <= bo::END && bo::T2S + 2 * ((NX + 7) * TW + 4 * SWQ) <= bo::END,
+                  "sweep: idle-lane operands beyond the arrays");
     int d = 2 * (n - 1);
     int i = (n - 1) + e, j = d - i;                              // entry e of the first anti-diagonal (only e = 0 exists there)
+#ifdef __CUDACC__
+    int oti = 2 * (i * TW + sub), otj = 2 * (j * TW + sub);      // T rows i and j (my quarter of the terms)
+    int oij = 2 * (i * n + j), oji = 2 * (j * n + i);            // entries (i, j) and (j, i)
+    const int ysub = 2 * (1 + sub) * n;
+#endif
     CPDP_LOOP for (; d >= 0; --d) {
         const bool valid = (i <= j) && (i >= 0);
-        const int ic = valid ? i : 0, jc = valid ? j : 0;
+#ifdef __CUDACC__
+        const double* ta = T2 + oti; const double* ya = Y + oij + ysub;
+        const double* tb = T2 + otj; const double* yb = Y + oji + ysub;
+        const double* cvp = Y + oij; const double* pvp = PVm + oij;
+#else
+        const int ic = valid ? i : 0, jc = valid ? j : 0;        // (host emulation: idle lanes read entry (0, 0) -- no stray reads)
         const double* ta = T2 + 2 * (ic * TW + sub); const double* ya = Y + 2 * ((ic + 1 + sub) * n + jc);
         const double* tb = T2 + 2 * (jc * TW + sub); const double* yb = Y + 2 * ((jc + 1 + sub) * n + ic);
         const double* cvp = Y + 2 * (ic * n + jc); const double* pvp = PVm + 2 * (ic * n + jc);
+#endif
         double pr[2 * SWQ], pi_[2 * SWQ];
         BDF_UNROLL for (int m = 0; m < SWQ; ++m) {
             const auto t1 = BDF_LD2(ta + 8 * m), y1 = BDF_LD2(ya + 8 * m * n);
@@ -768,13 +818,23 @@ CPDP_D void bdf_sweep(double* sm, const double c) {
             const double yr = rr * pv.x - ri * pv.y, yi = rr * pv.y + ri * pv.x;
             const bool st = valid && (sub == 0);
             double* dump = sm + bo::RU + 2 * tid;                 // (change_D's scratch: free during a Newton solve)
+#ifdef __CUDACC__
+            double* p1 = st ? Y + oij : dump;
+            double* p2 = (st && i != j) ? Y + oji : dump + 64;
+#else
             double* p1 = st ? Y + 2 * (i * n + j) : dump;
             double* p2 = (st && i != j) ? Y + 2 * (j * n + i) : dump + 64;
+#endif
             BDF_ST2(p1, yr, (i == j) ? 0.0 : yi);
             BDF_ST2(p2, yr, -yi);
         }
         // next anti-diagonal: d > n-1: the first row of the diagonal drops by one (i - 1, same j); else the column does
-        if (d > n - 1) --i; else --j;
+        const bool up = d > n - 1;
+        if (up) --i; else --j;
+#ifdef __CUDACC__
+        oti -= up ? 2 * TW : 0; otj -= up ? 0 : 2 * TW;
+        oij -= up ? 2 * n : 2; oji -= up ? 2 : 2 * n;
+#endif
         BDF_SYNC();
     }
 }
@@ -1173,6 +1233,7 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, CPDP_BDF_MINB) k_riccati_bdf(Aux
     int st = 0;
 #ifdef CPDP_BDF_TIMING
     long long tp[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (lane < 8) sm[bo::TS + lane] = 0.0;
     const long long tstart__ = clock64();
 #endif
     CPDP_LOOP for (int k = N; k >= 1 && st == 0; --k) {
@@ -1186,6 +1247,7 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, CPDP_BDF_MINB) k_riccati_bdf(Aux
         tp[8] = clock64() - tstart__;
         double* dst = a.Ua + (size_t)b * (N + 1) * NU * NP;
         for (int i = 0; i < 16; ++i) dst[i] = (double)tp[i];
+        for (int i = 0; i < 8; ++i) dst[16 + i] = sm[bo::TS + i];
     }
 #endif
     if (lane == 0) {

@@ -21,6 +21,8 @@ VARIANTS = {
     "l2s1": ["-DCPDP_BDF_LMUL_UNROLL=2", "-DCPDP_BDF_STENCIL_UNROLL=1"],
     "l1s1": ["-DCPDP_BDF_LMUL_UNROLL=1", "-DCPDP_BDF_STENCIL_UNROLL=1"],
     "l4s2": ["-DCPDP_BDF_LMUL_UNROLL=4", "-DCPDP_BDF_STENCIL_UNROLL=2"],
+    "r168": ["-DCPDP_BDF_MINB=12"],
+    "r128": ["-DCPDP_BDF_MINB=16"],
     "l13s1": ["-DCPDP_BDF_LMUL_UNROLL=13", "-DCPDP_BDF_STENCIL_UNROLL=1"],
 }
 PHASES = ["prepare", "rhs", "jacobian", "schur", "factor", "solve", "norm", "change_D", "total"]
@@ -72,7 +74,7 @@ def main():
             out = {"variant": v, "batch": B, "ms": [round(t, 3) for t in times],
                    "failed": int((aux["aux_status"] != 0).sum().item())}
             if "time" in v:
-                tp = aux["Ua"].reshape(B, -1)[:, :16].cpu().numpy()
+                tp = aux["Ua"].reshape(B, -1)[:, :24].cpu().numpy()
                 tot = tp[:, 8].mean()
                 out["cycles_total_mean"] = float(tot)
                 out["phase_share"] = {PHASES[i]: round(float(tp[:, i].mean() / tot), 4) for i in range(8)}
@@ -89,6 +91,10 @@ def main():
                 nsol = cnt[:, 0].mean() - 2 * a.n_grid
                 out["solve_cycles_per_call"] = {nm: float(tp[:, 10 + i].mean() / nsol) for i, nm in enumerate(
                     ["QtBQ", "stencil_in", "sweep", "stencil_out", "QYQt", "sym_W"])}
+                nj = cnt[:, 5].mean()
+                out["schur_cycles_per_call"] = {nm: float(tp[:, 16 + i].mean() / nj) for i, nm in enumerate(
+                    ["hessenberg", "qr_scans", "qr_scans_plus_chase", "rotations", "rotations_plus_packing"])}
+                out["counters_mean"] = {"rhs": cnt[:, 0].mean(), "steps": cnt[:, 1].mean(), "lu": cnt[:, 4].mean(), "jac": nj}
             print(json.dumps(out), flush=True)
 
 
