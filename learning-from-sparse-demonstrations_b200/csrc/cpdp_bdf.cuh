@@ -743,8 +743,7 @@ CPDP_D_NOINLINE bool bdf_factor(const double c) {
         }
         BDF_SYNC();
     }
-    bad = bdf_reduce(bad, true);
-    if (bad != 0.0) return false;
+    if (bdf_ballot(sm, bad != 0.0)) return false;
     if (isB) { BDF_UNROLL for (int i = 0; i < n; ++i) sm[bo::WT + (lane - 16) * QS + i] = XB[i * NCS + lane - 16]; }     // WT[k][i] = Winv[i][k]
     BDF_SYNC();
     return true;
@@ -1094,18 +1093,21 @@ CPDP_D int bdf_interval(double* sm, double* D, const AuxProblem& p, const double
                     BDF_SYNC();
                     BDF_T(1, bdf_rhs_smem(false)); ++cnt[0];
                     bdf_get_col(sm + bo::XB, lc, r);
-                    double fin = 0.0;
+                    bool fin = false;
                     BDF_UNROLL for (int i = 0; i < NX; ++i) {
-                        if (act && !(fabs(r[i]) < 1e300)) fin = 1.0;
+                        if (act && !(fabs(r[i]) < 1e300)) fin = true;
                         r[i] = c * r[i] - psi[i] - d[i];
                     }
-                    fin = bdf_reduce(fin, true);
-                    if (fin != 0.0) break;
+                    if (bdf_ballot(sm, fin)) break;
                     BDF_T(5, bdf_solve_cols(sm, c_lu, r BDF_TP_ARG));
                     double dy_norm; BDF_TB(6, dy_norm, bdf_norm_cols(r, isc, 1.0, act));
                     const bool have_rate = dy_norm_old >= 0.0;
                     const double rate = have_rate ? dy_norm / dy_norm_old : 0.0;
-                    if (have_rate && (rate >= 1 || bdf_pow(rate, (double)(BDF_NEWTON_MAXITER - k)) / (1 - rate) * dy_norm > newton_tol)) break;
+                    double rpow = rate;                                  // rate ** (NEWTON_MAXITER - k), exponent 3, 2 or 1
+                    if (BDF_NEWTON_MAXITER - k >= 2) rpow *= rate;
+                    if (BDF_NEWTON_MAXITER - k >= 3) rpow *= rate;
+                    static_assert(BDF_NEWTON_MAXITER == 4, "rate power above is written for exponents <= 3");
+                    if (have_rate && (rate >= 1 || rpow / (1 - rate) * dy_norm > newton_tol)) break;
                     BDF_UNROLL for (int i = 0; i < NX; ++i) { y[i] += r[i]; d[i] += r[i]; }
                     if (dy_norm == 0 || (have_rate && rate / (1 - rate) * dy_norm < newton_tol)) { converged = true; break; }
                     dy_norm_old = dy_norm;
