@@ -116,7 +116,7 @@ CPDP_API int cpdp_solve(void* ws, size_t ws_bytes, int B, int N, int S, double T
     for (int it = 0; it < total_rounds; ++it) {
         ++g_last_rounds;
         CPDP_LAUNCH(k_stage_adjoint, sms * 8, 128, 0, st, a);
-        CPDP_LAUNCH(k_stage_hessian, sms * 4, HESS_THREADS, 0, st, a);
+        CPDP_LAUNCH(k_stage_hessian, sms * CPDP_HESS_GRID_MULT, HESS_THREADS, 0, st, a);
         CPDP_LAUNCH(k_newton_step, sms * 16, NEWTON_THREADS, 0, st, a);      // persistent: strides over the active list
         CPDP_LAUNCH(k_compact, 1, COMPACT_THREADS, 0, st, a);
         if (rounds <= 0 && it >= 3) {     // adaptive mode: poll the active count (host sync)

@@ -205,17 +205,21 @@ CPDP_D void stage_adjoint_item(const SolveArgs& a, int b, int k) {
 // Thread j propagates column j of the forward sensitivity d(stage state)/d(x_k,u_k) through the 4S stages and
 // accumulates column j of  Hess = sum_s Sz_s' Hess_z(mu_s'f + w_s c) Sz_s ; writes [A B] and Hess.
 // ------------------------------------------------------------------------------------------------
+// CTA size: the kernel needs ~250 registers per thread, so an SM holds 256 threads of it whatever their grouping; small CTAs
+// (64 threads, four per SM) run out of phase with each other and overlap the arithmetic-bound model code of one with the
+// shared-memory-bound accumulation of another, which one 256-thread CTA serialises behind its barriers (41.5 -> 38.3 ms / solve)
 #ifndef CPDP_HESS_THREADS
-#define CPDP_HESS_THREADS 256
+#define CPDP_HESS_THREADS 64
+#endif
+#ifndef CPDP_HESS_GRID_MULT
+#define CPDP_HESS_GRID_MULT (4 * (256 / CPDP_HESS_THREADS))     // CTAs per SM in the grid (grid-stride loop over the interval groups)
 #endif
 constexpr int HESS_THREADS = CPDP_HESS_THREADS;
 constexpr int KPC = HESS_THREADS / NZ;          // intervals per CTA
+static_assert(KPC >= 1, "k_stage_hessian: a CTA must hold at least one interval (NZ threads)");
 
 #ifndef CPDP_HESS_MINB
-#define CPDP_HESS_MINB 1
-#endif
-#ifndef CPDP_HESS_ACC_UNROLL
-#define CPDP_HESS_ACC_UNROLL NZ         // (partial unrolling sends hz / Hc to local memory: dynamic indices)
+#define CPDP_HESS_MINB (256 / CPDP_HESS_THREADS)
 #endif
 CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian(SolveArgs a) {
     CPDP_SHARED double s_x[2][KPC][NX];        // double-buffered: the next stage's states / adjoints are fetched while this one computes
@@ -225,7 +229,9 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
     CPDP_SHARED double s_pd[KPC][NQT > 0 ? NQT : 1];
     constexpr int SXS = (NX + 1) & ~1;                 // even row length: the Hessian accumulation reads the rows with 128-bit loads
     CPDP_SHARED __align__(16) double s_S[KPC][NZ][SXS];
+    CPDP_SHARED double s_hzu[KPC][NZ][NU];     // control rows of each thread's Hessian-vector product (dynamic index in the accumulation)
     CPDP_SHARED int s_gi[KPC];                 // global interval index b*N+k of each slot, -1 if none
+    constexpr int HW = NZ / 2 + 1;
     const int tid = threadIdx.x;
     const int kk = tid / NZ, j = tid % NZ;
     const int total = *a.nact * a.N;
@@ -257,10 +263,19 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
         const bool mine = (kk < KPC) && (s_gi[kk < KPC ? kk : 0] >= 0);
         const int gi = mine ? s_gi[kk] : -1;
 
-        double Sx[NX], Sn[NX], dX[NX], df[NX], du[NU], hz[NZ], Hc[NZ];
+        // The Hessian is symmetric: thread j accumulates the HW entries (i, j), i = (j + w) mod NZ, w < HW, and mirrors them at
+        // the end -- every unordered pair {i, j} is covered once (for even NZ the pairs at distance NZ/2 twice: not mirrored).
+        double Sx[NX], Sn[NX], dX[NX], df[NX], du[NU], hz[NZ], Hc[HW];
+        const double* rowp[HW];                    // row i of this interval's stage sensitivities
+        int rowu[HW];                              // i - NX for the control rows, -1 for the state rows
+        for (int w = 0; w < HW; ++w) {
+            const int i = (j + w) % NZ;
+            rowp[w] = s_S[kk < KPC ? kk : 0][i];
+            rowu[w] = i >= NX ? i - NX : -1;
+            Hc[w] = 0.0;
+        }
         for (int i = 0; i < NX; ++i) { Sx[i] = (i == j) ? 1.0 : 0.0; df[i] = 0.0; }
         for (int i = 0; i < NU; ++i) du[i] = (NX + i == j) ? 1.0 : 0.0;
-        for (int i = 0; i < NZ; ++i) Hc[i] = 0.0;
 
         // stage states + adjoints of every interval of this group: fetched one stage ahead into registers, parked in the other
         // shared-memory buffer after the Hessian accumulation (the global-load latency hides behind the model code)
@@ -301,25 +316,32 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
                     for (int i = 0; i < NX; ++i) dX[i] = Sx[i] + ca * df[i];
                     Model::dir(s_x[cur][kk], s_u[kk], s_th[kk], s_pd[kk], s_mu[cur][kk], bco[st] * DT, dX, du, df, hz);
                     for (int i = 0; i < NX; ++i) s_S[kk][j][i] = dX[i];
+                    for (int i = 0; i < NU; ++i) s_hzu[kk][j][i] = hz[NX + i];      // (read back by this thread only)
                 }
                 __syncthreads();
                 if (mine) {
-                    CPDP_PRAGMA_UNROLL(CPDP_HESS_ACC_UNROLL) for (int i = 0; i < NZ; ++i) {
-                        double acc = (i >= NX) ? hz[i] : 0.0;
-                        const double* col = s_S[kk][i];
+                    // Hc[w] += hz[i] (control rows) + sum_e S[i][e] hz[e],  i = (j + w) mod NZ, e ascending.  The HW rows advance
+                    // together through e: their loads are issued back to back and the rows are independent sums, so neither the
+                    // shared-memory latency nor the add latency of one row's chain is exposed.
+                    double acc[HW];
+                    CPDP_PRAGMA_UNROLL(HW) for (int w = 0; w < HW; ++w) acc[w] = rowu[w] >= 0 ? s_hzu[kk][j][rowu[w] >= 0 ? rowu[w] : 0] : 0.0;
 #ifdef __CUDACC__
 #pragma unroll
-                        for (int e = 0; e + 1 < NX; e += 2) {
-                            const double2 c2 = *reinterpret_cast<const double2*>(col + e);
-                            acc += c2.x * hz[e];
-                            acc += c2.y * hz[e + 1];
-                        }
-                        if (NX & 1) acc += col[NX - 1] * hz[NX - 1];
-#else
-                        for (int e = 0; e < NX; ++e) acc += col[e] * hz[e];
-#endif
-                        Hc[i] += acc;
+                    for (int e = 0; e + 1 < NX; e += 2) {
+                        double2 c2[HW];
+#pragma unroll
+                        for (int w = 0; w < HW; ++w) c2[w] = *reinterpret_cast<const double2*>(rowp[w] + e);
+#pragma unroll
+                        for (int w = 0; w < HW; ++w) { acc[w] += c2[w].x * hz[e]; acc[w] += c2[w].y * hz[e + 1]; }
                     }
+                    if (NX & 1) {
+#pragma unroll
+                        for (int w = 0; w < HW; ++w) acc[w] += rowp[w][NX - 1] * hz[NX - 1];
+                    }
+#else
+                    for (int w = 0; w < HW; ++w) { for (int e = 0; e < NX; ++e) acc[w] += rowp[w][e] * hz[e]; }
+#endif
+                    CPDP_PRAGMA_UNROLL(HW) for (int w = 0; w < HW; ++w) Hc[w] += acc[w];
                     const double cb = bco[st] * DT;
                     for (int i = 0; i < NX; ++i) Sn[i] += cb * df[i];
                 }
@@ -334,7 +356,11 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
             double* AB = a.AB + (size_t)gi * NX * NZ;
             for (int i = 0; i < NX; ++i) AB[i * NZ + j] = Sx[i];
             double* H = a.H + (size_t)gi * NZ * NZ;
-            for (int i = 0; i < NZ; ++i) H[i * NZ + j] = Hc[i];
+            for (int w = 0; w < HW; ++w) {
+                const int i = (j + w) % NZ;
+                H[i * NZ + j] = Hc[w];
+                if (w != 0 && !(NZ % 2 == 0 && w == NZ / 2)) H[j * NZ + i] = Hc[w];
+            }
         }
     }
 }

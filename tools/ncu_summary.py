@@ -34,6 +34,15 @@ for ai in range(rng.num_actions()):
         "stall_per_issue": {k: m("smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % k) for k in
                             ("barrier", "wait", "short_scoreboard", "long_scoreboard", "no_instruction", "branch_resolving", "math_pipe_throttle", "not_selected")},
         "local_load_inst": m("sass__inst_executed_local_loads"), "local_store_inst": m("sass__inst_executed_local_stores"),
+        "shared_load_inst": m("smsp__inst_executed_op_shared_ld.sum"), "shared_store_inst": m("smsp__inst_executed_op_shared_st.sum"),
+        "shared_wavefronts": m("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+        "shared_bank_conflicts": m("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+        "lsu_pipe_pct": m("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+        "l1tex_data_pipe_pct": m("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+        "mio_throttle_per_issue": m("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"),
+        "lg_throttle_per_issue": m("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"),
+        "dispatch_stall_per_issue": m("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio"),
+        "elapsed_cycles_sm": m("sm__cycles_elapsed.avg"),
     }
     json.dump(d, open(out, "w"), indent=1)
     print(json.dumps(d))
