@@ -37,7 +37,7 @@ namespace CPDP_NS {
 constexpr int BDF_THREADS = 32;
 constexpr int NC = NX + NP;                      // columns of S = [P | W]: one lane each
 static_assert(NC <= 32, "k_riccati_bdf maps one lane per column of [P | W]");
-static_assert(NX <= 16 && NP <= 16, "warp sections map one lane per row/column and 16 + lane for the second half / the rows of Z");
+static_assert(NX <= 15 && NP <= 16, "warp sections map one lane per row/column and 16 + lane for the second half / the rows of Z; lane 31 must stay free for the bulge-chase fix-up");
 #ifndef CPDP_BDF_MINB
 #define CPDP_BDF_MINB 8
 #endif
@@ -444,6 +444,8 @@ CPDP_D bool schur_real_w0(double* sm, double* H, double* Z, double* vb) {
     const int lane = threadIdx.x;
     const double EPS = 2.220446049250313e-16;
 #define h_(i, j) H[(i) * n + (j)]
+    const int rw = lane & 15;                                      // lanes 0..15: row rw of H, lanes 16..31: row rw of Z
+    double* const Mrow = (rw < n) ? ((lane < 16) ? H : Z) + rw * n : vb;      // (lanes without a row: scratch nobody writes in the chase)
     for (int i = lane; i < n * n; i += 32) Z[i] = (i / n == i % n) ? 1.0 : 0.0;
     BDF_SYNC();
     // ---- Hessenberg form
@@ -471,17 +473,11 @@ CPDP_D bool schur_real_w0(double* sm, double* H, double* Z, double* vb) {
             }
         }
         BDF_SYNC();
-        if (lane < n) {                                            // H <- H (I - tau v v'), my row
-            double u = 0.0;
-            BDF_UNROLL for (int k = 0; k < n; ++k) u += h_(lane, k) * vb[k];
+        if (rw < n) {                                              // H <- H (I - tau v v') and Z <- Z (I - tau v v'): my row of H / of Z,
+            double u = 0.0;                                        // one instruction stream for both halves of the warp
+            BDF_UNROLL for (int k = 0; k < n; ++k) u += Mrow[k] * vb[k];
             u *= tau;
-            BDF_UNROLL for (int k = 0; k < n; ++k) h_(lane, k) -= u * vb[k];
-        } else if (lane >= 16 && lane < 16 + n) {
-            const int r_ = lane - 16;
-            double u = 0.0;
-            BDF_UNROLL for (int k = 0; k < n; ++k) u += Z[r_ * n + k] * vb[k];
-            u *= tau;
-            BDF_UNROLL for (int k = 0; k < n; ++k) Z[r_ * n + k] -= u * vb[k];
+            BDF_UNROLL for (int k = 0; k < n; ++k) Mrow[k] -= u * vb[k];
         }
         BDF_SYNC();
     }
@@ -558,29 +554,29 @@ CPDP_D bool schur_real_w0(double* sm, double* H, double* Z, double* vb) {
                 const double xx = 1.0 + fabs(p) * rs, yy = q * rs * sgn, zz = r * rs * sgn;
                 const double ixx = bdf_rcp(xx);                          // xx in [1, 2]
                 const double qn = yy * ixx, rn = zz * ixx;
-                if (lane >= k && lane < n) {
-                    double pp = h_(k, lane) + qn * h_(k + 1, lane);
-                    if (notlast) { pp += rn * h_(k + 2, lane); h_(k + 2, lane) -= pp * zz; }
-                    h_(k, lane) -= pp * xx;
-                    h_(k + 1, lane) -= pp * yy;
+                {   // rows k .. k+2 of my column (columns >= k).  Branch-free: idle lanes compute on column k and store nothing
+                    const bool on = lane >= k && lane < n;
+                    double* const col = on ? H + lane : Z;             // (idle lanes: column 0 of Z, which this phase does not write)
+                    const double a0 = col[k * n], a1 = col[(k + 1) * n], a2 = notlast ? col[(k + 2) * n] : 0.0;
+                    const double pp = (a0 + qn * a1) + rn * a2;         // (a2 = 0 in the last step: adds an exact zero)
+                    if (on && notlast) col[(k + 2) * n] = a2 - pp * zz;
+                    if (on) col[k * n] = a0 - pp * xx;
+                    if (on) col[(k + 1) * n] = a1 - pp * yy;
                 }
                 BDF_SYNC();
-                const int imax = (en < k + 3) ? en : k + 3;
-                if (lane <= imax) {
-                    double pp = xx * h_(lane, k) + yy * h_(lane, k + 1);
-                    if (notlast) { pp += zz * h_(lane, k + 2); h_(lane, k + 2) -= pp * rn; }
-                    h_(lane, k) -= pp;
-                    h_(lane, k + 1) -= pp * qn;
-                } else if (lane >= 16 && lane < 16 + n) {
-                    const int i = lane - 16;
-                    double pp = xx * Z[i * n + k] + yy * Z[i * n + k + 1];
-                    if (notlast) { pp += zz * Z[i * n + k + 2]; Z[i * n + k + 2] -= pp * rn; }
-                    Z[i * n + k] -= pp;
-                    Z[i * n + k + 1] -= pp * qn;
-                } else if (lane == 31) {
-                    // column k-1 below the diagonal is not touched by the two updates of this step
-                    if (k != m) { h_(k, k - 1) = -s; h_(k + 1, k - 1) = 0.0; if (notlast) h_(k + 2, k - 1) = 0.0; }
-                    else if (l != m) h_(k, k - 1) = -h_(k, k - 1);
+                {   // columns k .. k+2 of my row of H (rows <= imax) / of Z: one stream, branch-free
+                    const int imax = (en < k + 3) ? en : k + 3;
+                    const bool on = lane < 16 ? (rw <= imax) : (rw < n);
+                    const double z0 = Mrow[k], z1 = Mrow[k + 1], z2 = notlast ? Mrow[k + 2] : 0.0;
+                    const double pp = (xx * z0 + yy * z1) + zz * z2;
+                    if (on && notlast) Mrow[k + 2] = z2 - pp * rn;
+                    if (on) Mrow[k] = z0 - pp;
+                    if (on) Mrow[k + 1] = z1 - pp * qn;
+                    // column k-1 below the diagonal (every lane read it above, before the barrier; the two updates do not touch it)
+                    if (lane == 31) {
+                        if (k != m) { h_(k, k - 1) = -s; h_(k + 1, k - 1) = 0.0; if (notlast) h_(k + 2, k - 1) = 0.0; }
+                        else if (l != m) h_(k, k - 1) = -h_(k, k - 1);
+                    }
                 }
                 BDF_SYNC();
             }
