@@ -185,7 +185,7 @@ def flop_model(info, n, m, r, N, S, iters_sum, B, cnt, mode):
     nz = n + m
     stages = 4 * S
     per_int = stages * (2 * info["ops_fc"] + info["ops_hgrad"] + 8 * n)                     # k_stage_adjoint
-    per_int += stages * nz * (info["ops_dir"] + 2 * nz * n + 6 * n)                         # k_stage_hessian
+    per_int += stages * nz * (info["ops_dir"] + 2 * (nz // 2 + 1) * n + 6 * n)              # k_stage_hessian (symmetric accumulation)
     per_int += 2 * n * n * nz + 2 * nz * nz * n + 2 * m * m * (n + 1) + 2 * n * n * m + 4 * n * nz + stages * info["ops_fc"]
     solve = iters_sum * N * per_int
     nnzx, nnzu = info["nnz_fx"], info["nnz_fu"]
