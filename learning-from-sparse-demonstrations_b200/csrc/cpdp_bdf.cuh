@@ -106,12 +106,14 @@ constexpr int GHM = XB + NX * NCS;               // fu Huu^{-1}, [NX][NU]
 constexpr int YPM = GHM + NX * NU;               // Huu^{-1} Y, [NU][NX]
 constexpr int ROT = YPM + NU * NX;               // block rotations G: ga | gbr | gbi | partner   (4 x NX)
 constexpr int RU = (ROT + 4 * NX + 1) & ~1;                 // change_D: RU | R | U, 6 x 6 each (also Householder vector scratch, sweep store dump: 128)
-constexpr int FLAG = RU + 128;                   // 2 ints
+constexpr int FLAG = RU + 128;                   // 3 ints: prepare ok | Schur ok | first node row held in NODE
+constexpr int NODE = FLAG + 2;                   // the two node rows (x, u, lambda) bracketing the current grid interval
+constexpr int NODE_W = 2 * NX + NU;
 #ifdef CPDP_BDF_TIMING
-constexpr int TS = FLAG + 2;                     // developer timing build: Schur sub-phase clocks (8)
+constexpr int TS = NODE + ((2 * NODE_W + 1) & ~1);   // developer timing build: Schur sub-phase clocks (8)
 constexpr int END = TS + 8;
 #else
-constexpr int END = FLAG + 2;
+constexpr int END = NODE + ((2 * NODE_W + 1) & ~1);
 #endif
 static_assert(Y2 % 2 == 0 && T2S % 2 == 0 && TD % 2 == 0 && PV % 2 == 0 && RU % 2 == 0, "complex arrays are read with 128-bit loads");
 }  // namespace bo
@@ -221,13 +223,38 @@ CPDP_D void bdf_get_col(const double* buf, int c, double (&v)[NX]) {
 // ------------------------------------------------------------------------------------------------
 // PMP matrices at time t (CPDP.py:317-323: opt_sol(t) by linear interp1d, then the derivative set of diffPMP)
 // ------------------------------------------------------------------------------------------------
+// rows lo, lo + 1 of the node tables X, U, Lam for the grid interval that starts (backwards) at t0: one batch of loads per
+// interval instead of two dependent global loads per lane in every step's bdf_prepare
+CPDP_D void bdf_stage_nodes(double* sm, const AuxProblem& p, const double t0) {
+    const int lane = threadIdx.x;
+    const int lo = interp_lo(t0, p.dt, p.N);
+    BDF_SYNC();
+    CPDP_LOOP for (int q = lane; q < 2 * bo::NODE_W; q += BDF_THREADS) {
+        const int row = lo + q / bo::NODE_W, e = q % bo::NODE_W;
+        sm[bo::NODE + q] = (e < NX) ? p.X[(size_t)row * NX + e]
+                         : (e < NX + NU) ? p.U[(size_t)row * NU + e - NX] : p.Lam[(size_t)row * NX + e - NX - NU];
+    }
+    if (lane == 0) ((int*)(sm + bo::FLAG))[2] = lo;
+    BDF_SYNC();
+}
 CPDP_D_NOINLINE bool bdf_prepare(const AuxProblem p, const double t) {
     BDF_SM();
     const int lane = threadIdx.x;
     BDF_SYNC();
-    CPDP_LOOP for (int q = lane; q < 2 * NX + NU; q += BDF_THREADS) sm[bo::XUL + q] = xul_at(p, t, q);
-    BDF_SYNC();
     int* flag = (int*)(sm + bo::FLAG);
+    {   // xul_at through the interval's staged node rows (bdf_stage_nodes); a time outside them (the interval's end point belongs
+        // to the previous pair of rows under interp1d's rule) reads global memory.  Same arithmetic either way.
+        const int lo = interp_lo(t, p.dt, p.N);
+        const bool hit = lo == flag[2];
+        const double xlo = p.dt * lo, xhi = p.dt * (lo + 1);
+        CPDP_LOOP for (int q = lane; q < bo::NODE_W; q += BDF_THREADS) {
+            double v;
+            if (hit) v = interp_val(sm[bo::NODE + q], sm[bo::NODE + bo::NODE_W + q], xlo, xhi, t);
+            else v = xul_at(p, t, q);
+            sm[bo::XUL + q] = v;
+        }
+    }
+    BDF_SYNC();
     if (lane == 0) flag[0] = pmp_eval(p, sm + bo::XUL, sm + bo::M, t) ? 1 : 0;
     BDF_SYNC();
     return flag[0] != 0;
@@ -977,6 +1004,7 @@ CPDP_D int bdf_interval(double* sm, double* D, const AuxProblem& p, const double
     const double dir = (t1 >= t0) ? 1.0 : -1.0;
     const double EPS = 2.220446049250313e-16;
 #define D_(row, i) D[((size_t)(row) * NX + (i)) * NC + lc]
+    bdf_stage_nodes(sm, p, t0);
     // ---- __init__ (bdf.py:200-257)
     { bool okp__; BDF_TB(0, okp__, bdf_prepare(p, t0)); if (!okp__) return 2; }
     double f0[NX];
