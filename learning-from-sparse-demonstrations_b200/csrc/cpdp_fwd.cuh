@@ -32,7 +32,10 @@ constexpr int TMS = XS + NX * NPS;                              // [8]
 constexpr int RED = TMS + 8;                                    // [66]
 constexpr int FLAG = RED + 66;
 constexpr int TAB = FLAG + 2;                                   // Dormand-Prince A[6][5] (a dynamically indexed local table would live in local memory)
-constexpr int END = TAB + 30;
+constexpr int MBAR = (TAB + 30 + 1) & ~1;                                // mbarrier of the node-row ring (8 B) | ring_lo, ring_hi (2 ints)
+constexpr int RING = MBAR + 2;                                  // [3][NYR] rows of the P / W node table, row r in slot r % 3
+constexpr int END = RING + ((3 * NYR + 1) & ~1);
+static_assert(RING % 2 == 0, "bulk copies need a 16-byte aligned destination");
 }  // namespace fo
 constexpr size_t FW_SMEM_BYTES = (size_t)fo::END * sizeof(double);
 constexpr int FWS_FXC = 0, FWS_FUC = Model::FX_nnz, FWS_FE = FWS_FUC + Model::FU_nnz, FWS_HY = FWS_FE + NX * NP, FWS_HZ = FWS_HY + NU * NX;
@@ -48,6 +51,64 @@ CPDP_D_NOINLINE double fw_reduce(double v, bool is_max) {
     CPDP_DYN_SMEM(sm);
     return block_reduce(v, sm + fo::RED, is_max);
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Node-row ring.  The forward right-hand side interpolates P, W between the two node rows that bracket the stage time; the rows of
+// grid interval k (2.9 KB for the quadrotor) are the same for every stage of every step of that interval.  Row k+2 is fetched into
+// shared memory by the TMA engine (cp.async.bulk, completion on an mbarrier) while interval k integrates; fw_prepare reads the ring
+// and falls back to global memory for a row that is not in it.  Rows whose byte size is not a multiple of 16 (odd NYR) and the host
+// emulation copy with plain loads.
+// ------------------------------------------------------------------------------------------------
+constexpr bool FW_RING_TMA = (NYR % 2 == 0);
+CPDP_D unsigned fw_smem_addr(const void* ptr) {
+#ifdef __CUDACC__
+    return (unsigned)__cvta_generic_to_shared(ptr);
+#else
+    (void)ptr; return 0u;
+#endif
+}
+// rows [row, row + nrows) -> their slots (contiguous in the ring: the caller never wraps); tma: this launch may use bulk copies
+CPDP_D void fw_ring_issue(double* sm, const AuxProblem& p, const int row, const int nrows, const bool tma) {
+    double* dst = sm + fo::RING + (row % 3) * NYR;
+    const double* src = p.PW + (size_t)row * NYR;
+#ifdef __CUDACC__
+    if (tma) {
+        if (threadIdx.x == 0) {
+            const unsigned bar = fw_smem_addr(sm + fo::MBAR), bytes = (unsigned)(nrows * NYR * sizeof(double));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(fw_smem_addr(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+        }
+        return;
+    }
+#else
+    (void)tma;
+#endif
+    CPDP_LOOP for (int q = threadIdx.x; q < nrows * NYR; q += FW_THREADS) dst[q] = src[q];
+}
+// the copy issued `parity` completions ago ... has landed (tma) / is visible to the warp (plain copy)
+CPDP_D void fw_ring_wait(double* sm, const unsigned parity, const bool tma) {
+#ifdef __CUDACC__
+    if (tma) {
+        const unsigned bar = fw_smem_addr(sm + fo::MBAR);
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        }
+        return;
+    }
+#else
+    (void)parity; (void)tma;
+#endif
+    BDF_SYNC();
+}
+// row `lo` and `lo + 1` of the node table: ring slots when both are held, global memory otherwise
+CPDP_D void fw_rows(const double* sm, const AuxProblem& p, const int lo, const double*& P0, const double*& P1) {
+    const int* rg = (const int*)(sm + fo::MBAR) + 2;
+    if (lo >= rg[0] && lo + 1 <= rg[1]) { P0 = sm + fo::RING + (lo % 3) * NYR; P1 = sm + fo::RING + ((lo + 1) % 3) * NYR; }
+    else { P0 = p.PW + (size_t)lo * NYR; P1 = P0 + NYR; }
 }
 
 // Stage data for `cnt` times tms[0..cnt): (x, u, lambda) by interp1d, Model::pmp_fwd on lane s, then the columns of
@@ -91,7 +152,8 @@ CPDP_D_NOINLINE bool fw_prepare(const AuxProblem p, const int cnt) {
         const double t = tms[s];
         const int lo = interp_lo(t, p.dt, p.N);
         const double xlo = p.dt * lo, xhi = p.dt * (lo + 1);
-        const double* P0 = p.PW + (size_t)lo * NYR; const double* P1 = P0 + NYR;
+        const double* P0; const double* P1;
+        fw_rows(sm, p, lo, P0, P1);
         double* sl = sm + fo::SL + s * FW_SLOT;
         const double* sc = sm + fo::SCR + s * FW_SCR;
         const double* fuc = sl + FWS_FUC;
@@ -281,6 +343,23 @@ CPDP_GLOBAL void __launch_bounds__(FW_THREADS) k_aux_forward(AuxArgs a) {
     CPDP_LOOP for (int q = k; q < NSLOT * FW_SLOT; q += FW_THREADS) sm[fo::SL + q] = 0.0;       // structural zeros of fe
     CPDP_LOOP for (int q = k; q < NSLOT * FW_SCR; q += FW_THREADS) sm[fo::SCR + q] = 0.0;      //   and of Hxu, Hue, Huu
     if (k < 30) sm[fo::TAB + k] = dp_A(k / 5, k % 5);
+    // node-row ring: rows 0 and 1 now, row node + 2 while interval `node` integrates
+    int* rg = (int*)(sm + fo::MBAR) + 2;                        // ring_lo, ring_hi
+#ifdef __CUDACC__
+    const bool tma = FW_RING_TMA && (((size_t)p.PW & 15) == 0);
+    if (tma && k == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(fw_smem_addr(sm + fo::MBAR)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#else
+    const bool tma = false;
+#endif
+    if (k == 0) { rg[0] = 0; rg[1] = -1; }
+    BDF_SYNC();
+    unsigned n_issued = 0, n_waited = 0;                        // copies requested / consumed (mbarrier phase = count & 1)
+    fw_ring_issue(sm, p, 0, 2, tma); ++n_issued;                // (N >= 1: rows 0 and 1 exist)
+    fw_ring_wait(sm, n_waited & 1u, tma); ++n_waited;
+    if (k == 0) rg[1] = 1;
     double y[NX];
     BDF_UNROLL for (int i = 0; i < NX; ++i) y[i] = 0.0;
     if (act) { BDF_UNROLL for (int i = 0; i < NX; ++i) Xa[i * NP + kc] = 0.0; }
@@ -289,6 +368,10 @@ CPDP_GLOBAL void __launch_bounds__(FW_THREADS) k_aux_forward(AuxArgs a) {
     CPDP_LOOP for (int node = 0; node <= N && st == 0; ++node) {
         // stage data of the node time in slot 0: aux control at the node (CPDP.py:363-364,370-378) and, for node < N, the first
         // derivative of the next interval
+        if (node >= 1 && node + 1 <= N) {                       // row node + 1, requested while the previous interval ran
+            fw_ring_wait(sm, n_waited & 1u, tma); ++n_waited;
+            if (k == 0) rg[1] = node + 1;
+        }
         if (k == 0) sm[fo::TMS] = p.dt * node;
         if (!fw_prepare(p, 1)) { st = 2; break; }
         if (act) {
@@ -300,10 +383,17 @@ CPDP_GLOBAL void __launch_bounds__(FW_THREADS) k_aux_forward(AuxArgs a) {
             }
         }
         if (node == N) break;
+        if (node + 2 <= N) {                                    // its slot holds row node - 1, last read by the prepare above
+            BDF_SYNC();
+            if (k == 0 && node >= 1) rg[0] = node;
+            BDF_SYNC();
+            fw_ring_issue(sm, p, node + 2, 1, tma); ++n_issued;
+        }
         st = fw_interval(sm, p, p.dt * node, p.dt * (node + 1), a.rtol_f, a.atol_f, y, nrhs, nsteps);
         if (act) { BDF_UNROLL for (int i = 0; i < NX; ++i) Xa[(size_t)(node + 1) * NYF + i * NP + kc] = y[i]; }
         BDF_SYNC();
     }
+    while (n_waited < n_issued) { fw_ring_wait(sm, n_waited & 1u, tma); ++n_waited; }       // (a failed interval leaves its prefetch in flight)
     if (k == 0) { a.aux_status[b] = st; a.counters[b * NCOUNTERS + 2] = nrhs; a.counters[b * NCOUNTERS + 3] = nsteps; }
 #ifdef __CUDACC__
     __threadfence_block();
