@@ -800,9 +800,19 @@ CPDP_D void bdf_sweep(double* sm, const double c) {
     CPDP_LOOP for (; d >= 0; --d) {
         const bool valid = (i <= j) && (i >= 0);
 #ifdef __CUDACC__
+        // (idle lanes take their Y operands from the read-only arrays behind Y2 -- T2S, TD, PV: finite values, no store of this
+        //  sweep lands there -- so no lane reads an entry another lane writes on the same anti-diagonal)
+#ifdef CPDP_BDF_SWEEP_UNCLAMPED      // (developer A/B switch: idle lanes read wherever their stepped offsets point)
         const double* ta = T2 + oti; const double* ya = Y + oij + ysub;
         const double* tb = T2 + otj; const double* yb = Y + oji + ysub;
         const double* cvp = Y + oij; const double* pvp = PVm + oij;
+#else
+        const int rij = valid ? oij : 2 * n * n, rji = valid ? oji : 2 * n * n;
+        const double* ta = T2 + (valid ? oti : 0); const double* ya = Y + rij + ysub;
+        const double* tb = T2 + (valid ? otj : 0); const double* yb = Y + rji + ysub;
+        const double* cvp = Y + ((valid && sub == 0) ? oij : 2 * n * n);      // (the right-hand side entry: read by the lane that stores)
+        const double* pvp = PVm + oij;
+#endif
 #else
         const int ic = valid ? i : 0, jc = valid ? j : 0;        // (host emulation: idle lanes read entry (0, 0) -- no stray reads)
         const double* ta = T2 + 2 * (ic * TW + sub); const double* ya = Y + 2 * ((ic + 1 + sub) * n + jc);

@@ -17,10 +17,15 @@ ab = synthetic.robotarm_batch(2)
 cases["robotarm"] = dict(n_grid=6, x0=ab["x0"], T=1.0, th=ab["theta"], taus=ab["taus"], wp=ab["wp"], sel=ab["sel"])
 rb = synthetic.rocket_batch(2)
 cases["rocket"] = dict(n_grid=4, x0=rb["x0"], T=3.0, th=rb["theta0"], taus=np.array([0.75, 2.0]), wp=np.zeros((2, 2, 7)), sel=rb["sel"])
+qb = synthetic.quad_batch(2)      # (its node rows are a multiple of 16 bytes: the forward sweep's bulk-copy ring is active)
+cases["quadrotor"] = dict(n_grid=4, x0=qb["x0"], T=1.0, th=qb["theta"], taus=qb["taus"], wp=qb["wp"], sel=qb["sel"], pdata=qb["goal"])
+only = sys.argv[1:]
 for name, c in cases.items():
+    if only and name not in only:
+        continue
     oc = standard.STANDARD[name](n_grid=c["n_grid"])
     oc.build(name=oc.lib_name)
     for mode in (oc.MODE_BDF, oc.MODE_RK45):
-        red, sol, aux = oc.gradIterBatch(c["x0"], c["T"], c["th"], c["taus"], c["wp"], c["sel"], mode=mode)
+        red, sol, aux = oc.gradIterBatch(c["x0"], c["T"], c["th"], c["taus"], c["wp"], c["sel"], mode=mode, pdata=c.get("pdata"))
         torch.cuda.synchronize()
         print(name, "mode", mode, "status", sol["status"].tolist(), "aux", aux["aux_status"].tolist(), "counters", aux["counters"][0].tolist())
