@@ -53,33 +53,53 @@ def build_model_library(name, header_text, force=False, verbose=False):
     hdr = os.path.join(GEN_DIR, "model_%s.cuh" % name)
     so = os.path.join(LIB_DIR, "libcpdp_%s.so" % name)
     stamp = so + ".stamp"
-    digest = hashlib.sha1((header_text + _sources_digest() + " ".join(NVCC_FLAGS)).encode()).hexdigest()
-    # up to date?  The digest of (model header, kernel sources, flags) is compiled INTO the library (cpdp_build_digest), so a
-    # prebuilt .so is recognised wherever it travels without any side file (git-ignored stamp files do not reach a GPU box).
-    if not force and not EXTRA_NVCC_FLAGS and os.path.exists(so):
+    digest = hashlib.sha1((header_text + _sources_digest() + " ".join(NVCC_FLAGS + EXTRA_NVCC_FLAGS)).encode()).hexdigest()
+
+    def up_to_date():
+        # The digest of (model header, kernel sources, all flags) is compiled INTO the library (cpdp_build_digest), so a prebuilt
+        # .so is recognised wherever it travels without any side file (git-ignored stamp files do not reach a GPU box), and a
+        # tuning build (CPDP_EXTRA_NVCC_FLAGS) is never mistaken for the default one.
+        if force or not os.path.exists(so):
+            return False
         with open(so, "rb") as f:
-            if (_DIGEST_MARK + digest).encode() in f.read():
-                return so
+            return (_DIGEST_MARK + digest).encode() in f.read()
+
+    if up_to_date():
+        return so
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise CpdpError("libcpdp_%s.so is missing and nvcc was not found; the CUDA extension is required "
                         "(there is no CPU fallback)" % name)
-    with open(hdr, "w") as f:
-        f.write(header_text)
-    ns = "cpdp_" + "".join(ch if ch.isalnum() else "_" for ch in name)
-    cmd = [nvcc] + NVCC_FLAGS + EXTRA_NVCC_FLAGS + ["-I", CSRC, "-DCPDP_NS=%s" % ns, "-DCPDP_MODEL_HEADER=\"%s\"" % hdr,
-                                 "-DCPDP_BUILD_DIGEST=\"%s%s\"" % (_DIGEST_MARK, digest),
-                                 os.path.join(CSRC, "cpdp_lib.cu"), "-o", so]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise CpdpError("nvcc failed for model %s:\n%s\n%s" % (name, r.stdout, r.stderr))
-    if verbose:
-        print(r.stderr)
-    with open(stamp, "w") as f:
-        f.write(digest)
+    # One builder at a time per library (every rank of a torchrun job calls build()): the others wait on the lock and then find
+    # the finished file.  The compiler writes to a temporary name; the rename is atomic, so no process ever maps a partial file.
+    import fcntl
+    with open(so + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and up_to_date():
+                return so
+            with open(hdr, "w") as f:
+                f.write(header_text)
+            ns = "cpdp_" + "".join(ch if ch.isalnum() else "_" for ch in name)
+            tmp = "%s.tmp%d" % (so, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + EXTRA_NVCC_FLAGS + ["-I", CSRC, "-DCPDP_NS=%s" % ns, "-DCPDP_MODEL_HEADER=\"%s\"" % hdr,
+                                         "-DCPDP_BUILD_DIGEST=\"%s%s\"" % (_DIGEST_MARK, digest),
+                                         os.path.join(CSRC, "cpdp_lib.cu"), "-o", tmp]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd))
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise CpdpError("nvcc failed for model %s:\n%s\n%s" % (name, r.stdout, r.stderr))
+            if verbose:
+                print(r.stderr)
+            os.replace(tmp, so)
+            with open(stamp, "w") as f:
+                f.write(digest)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return so
 
 
