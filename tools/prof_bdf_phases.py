@@ -22,6 +22,7 @@ VARIANTS = {
     "l1s1": ["-DCPDP_BDF_LMUL_UNROLL=1", "-DCPDP_BDF_STENCIL_UNROLL=1"],
     "l4s2": ["-DCPDP_BDF_LMUL_UNROLL=4", "-DCPDP_BDF_STENCIL_UNROLL=2"],
     "unclamped": ["-DCPDP_BDF_SWEEP_UNCLAMPED"],
+    "prev": [],                                  # (a library built by hand from another revision of the sources, for A/B runs)
     "l2": ["-DCPDP_BDF_LMUL_UNROLL=2"],
     "l4": ["-DCPDP_BDF_LMUL_UNROLL=4"],
     "r168": ["-DCPDP_BDF_MINB=12"],
