@@ -9,11 +9,16 @@ ap.add_argument("--name", default="quadrotor")
 ap.add_argument("--batch", type=int, default=4096)
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--build-only", action="store_true")
+ap.add_argument("--no-build", action="store_true", help="load lib/libcpdp_<name>.so as it is (A/B runs against a library built from another revision)")
 a = ap.parse_args()
 import lfsd_b200  # noqa
 from lfsd_b200 import standard, synthetic
 oc = standard.quadrotor_oc(n_grid=50)
-oc.build(name=a.name)
+if a.no_build:
+    from lfsd_b200 import _capi
+    oc._lib = _capi.CpdpLib(os.path.join(_capi.LIB_DIR, "libcpdp_%s.so" % a.name))
+else:
+    oc.build(name=a.name)
 if a.build_only:
     sys.exit(0)
 import torch
