@@ -189,12 +189,12 @@ class COCSys:
         self.ddhxe = jacobian(self.dhx, self.auxvar)
 
     def raccatiODE(self):
-        """CPDP.py:253-276.  The Riccati right-hand side lives in the compiled kernels (csrc/cpdp_aux.cuh,
-        ``riccati_rhs``); this only makes sure the model is compiled."""
+        """CPDP.py:253-276.  The Riccati right-hand side lives in the compiled kernels (csrc/cpdp_bdf.cuh,
+        ``bdf_rhs_cols``); this only makes sure the model is compiled."""
         self.build()
 
     def auxSysODE(self):
-        """CPDP.py:281-298 (kernel: ``forward_rhs``)."""
+        """CPDP.py:281-298 (kernel: ``fw_rhs``, csrc/cpdp_fwd.cuh)."""
         self.build()
 
     # ------------------------------------------------------------------ compilation

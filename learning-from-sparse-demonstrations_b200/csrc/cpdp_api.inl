@@ -157,11 +157,11 @@ static int cpdp_aux_impl(void* ws, size_t ws_bytes, int B, int N, int S, double 
     a.taus = taus; a.taus_stride = taus_stride; a.wp = wp;
     a.loss = loss; a.dtheta = dtheta; a.solve_status = solve_status; a.aux_status = aux_status; a.counters = counters;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t ric_bytes = rk_smem_bytes<false>(), fwd_bytes = FW_SMEM_BYTES;
+    const size_t fwd_bytes = FW_SMEM_BYTES;
     if (phases & 1) {
         if (mode == 0) {
-            CPDP_PREPARE_SMEM(k_riccati_rk45, ric_bytes);
-            CPDP_LAUNCH(k_riccati_rk45, B, AUX_THREADS, ric_bytes, st, a);
+            CPDP_PREPARE_SMEM(k_riccati_rk45, RKW_SMEM_BYTES);
+            CPDP_LAUNCH(k_riccati_rk45, B, BDF_THREADS, RKW_SMEM_BYTES, st, a);
         } else {
             size_t bdf_bytes = BDF_SMEM_BYTES;
 #ifdef CPDP_BDF_OCCUPANCY_KNOB

@@ -1293,4 +1293,184 @@ CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, CPDP_BDF_MINB) k_riccati_bdf(Aux
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_riccati_rk45: the backward sweep with scipy's RK45 (mode 0: `oracle_tight`, COCSys_TimeVarying as shipped, CPDP.py:740) in the
+// shape of k_riccati_bdf -- one warp per problem, lane c owns column c of S = [P | W] in registers, the right-hand side is
+// bdf_prepare + bdf_rhs_smem (bitwise symmetric P block), the seven stage derivatives of Dormand-Prince live in shared memory
+// (over the arrays only the Newton solve of the BDF sweep uses, when they fit).  Control logic: rk.py:14-16, 111-170 and
+// common.py:63-134, statement for statement as rk45_interval of cpdp_aux.cuh (the first version, 64-thread CTAs on a packed
+// state in shared memory); the norms run over the full n x (n + r) state, as scipy's do.
+// ------------------------------------------------------------------------------------------------
+constexpr int RKW_K_DOUBLES = 7 * NX * NC;
+constexpr bool RKW_K_OVERLAID = RKW_K_DOUBLES <= bo::XA - bo::Q;
+constexpr int RKW_K = RKW_K_OVERLAID ? bo::Q : ((bo::END + 1) & ~1);
+constexpr int RKW_SMEM_DOUBLES = RKW_K_OVERLAID ? bo::END : RKW_K + RKW_K_DOUBLES;
+constexpr size_t RKW_SMEM_BYTES = (size_t)RKW_SMEM_DOUBLES * sizeof(double);
+
+// K[stage] = f(t, yin); with_prepare = false reuses the PMP matrices of the previous call (same time)
+CPDP_D bool rkw_rhs(double* sm, const AuxProblem& p, const double t, const bool with_prepare, const double (&yin)[NX], const int stage,
+                    const bool act, const int lc) {
+    if (with_prepare && !bdf_prepare(p, t)) return false;
+    if (act) bdf_put(sm + bo::XB, lc, yin);
+    BDF_SYNC();
+    bdf_rhs_smem(true);
+    if (act) { BDF_UNROLL for (int i = 0; i < NX; ++i) sm[RKW_K + (stage * NX + i) * NC + lc] = sm[bo::XB + i * NCS + lc]; }
+    BDF_SYNC();
+    return true;
+}
+
+CPDP_D int rkw_interval(double* sm, const AuxProblem& p, const double t0, const double t1, const double rtol, const double atol,
+                        double (&y)[NX], int& nrhs, int& nsteps) {
+    const int lane = threadIdx.x;
+    const bool act = lane < NC;
+    const int lc = act ? lane : 0;
+    const double dir = (t1 >= t0) ? 1.0 : -1.0;
+    const double NF = (double)NFULL_R;
+#define K_(s_, i_) sm[RKW_K + ((s_) * NX + (i_)) * NC + lc]
+    bdf_stage_nodes(sm, p, t0);
+    if (!rkw_rhs(sm, p, t0, true, y, 0, act, lc)) return 2;
+    ++nrhs;
+    double h_abs;
+    {   // select_initial_step (common.py:68-134), order = 4
+        const double interval_length = fabs(t1 - t0);
+        double a0 = 0.0, a1 = 0.0;
+        if (act) {
+            BDF_UNROLL for (int i = 0; i < NX; ++i) {
+                const double sc = atol + fabs(y[i]) * rtol;
+                const double f = K_(0, i);
+                a0 += (y[i] / sc) * (y[i] / sc);
+                a1 += (f / sc) * (f / sc);
+            }
+        }
+        const double d0 = sqrt(bdf_reduce(a0, false) / NF);
+        const double d1 = sqrt(bdf_reduce(a1, false) / NF);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, interval_length);
+        double ys[NX];
+        BDF_UNROLL for (int i = 0; i < NX; ++i) ys[i] = act ? y[i] + h0 * dir * K_(0, i) : 0.0;
+        if (!rkw_rhs(sm, p, t0 + h0 * dir, true, ys, 1, act, lc)) return 2;          // f1 parked in K[1]
+        ++nrhs;
+        double a2 = 0.0;
+        if (act) {
+            BDF_UNROLL for (int i = 0; i < NX; ++i) {
+                const double sc = atol + fabs(y[i]) * rtol;
+                const double v = (K_(1, i) - K_(0, i)) / sc;
+                a2 += v * v;
+            }
+        }
+        const double d2 = sqrt(bdf_reduce(a2, false) / NF) / h0;
+        double h1;
+        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+        else h1 = bdf_pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
+        h_abs = fmin(fmin(100 * h0, h1), interval_length);
+    }
+    double t = t0;
+    while (dir * (t - t1) < 0) {
+        const double min_step = 10 * fabs(nextafter(t, dir * (double)INFINITY) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false;
+        double t_new = t;
+        double yn[NX];
+        while (true) {
+            if (h_abs < min_step) return 1;
+            double h = h_abs * dir;
+            t_new = t + h;
+            if (dir * (t_new - t1) > 0) t_new = t1;
+            h = t_new - t;
+            h_abs = fabs(h);
+            BDF_UNROLL for (int st = 1; st < 6; ++st) {
+                double ys[NX];
+                BDF_UNROLL for (int i = 0; i < NX; ++i) {
+                    double acc = 0.0;
+                    BDF_UNROLL for (int j = 0; j < st; ++j) acc += (act ? K_(j, i) : 0.0) * dp_A(st, j);
+                    ys[i] = y[i] + acc * h;
+                }
+                if (!rkw_rhs(sm, p, t + dp_C(st) * h, true, ys, st, act, lc)) return 2;
+                ++nrhs;
+            }
+            BDF_UNROLL for (int i = 0; i < NX; ++i) {
+                double acc = 0.0;
+                BDF_UNROLL for (int j = 0; j < 6; ++j) acc += (act ? K_(j, i) : 0.0) * dp_B(j);
+                yn[i] = y[i] + h * acc;
+            }
+            if (!rkw_rhs(sm, p, t + dp_C(5) * h, false, yn, 6, act, lc)) return 2;     // (the time of stage 5: its PMP matrices are in place)
+            ++nrhs;
+            double ae = 0.0;
+            bool fin = false;
+            if (act) {
+                BDF_UNROLL for (int i = 0; i < NX; ++i) {
+                    double acc = 0.0;
+                    BDF_UNROLL for (int j = 0; j < 7; ++j) acc += K_(j, i) * dp_E(j);
+                    const double sc = atol + fmax(fabs(y[i]), fabs(yn[i])) * rtol;
+                    const double v = acc * h / sc;
+                    ae += v * v;
+                    if (!(fabs(yn[i]) < 1e300)) fin = true;
+                }
+            }
+            const double error_norm = sqrt(bdf_reduce(ae, false) / NF);
+            if (bdf_ballot(sm, fin) || !(error_norm == error_norm)) return 2;
+            ++nsteps;
+            if (error_norm < 1) {
+                double factor = (error_norm == 0) ? 10.0 : fmin(10.0, 0.9 * bdf_pow(error_norm, -0.2));
+                if (rejected) factor = fmin(1.0, factor);
+                h_abs *= factor;
+                break;
+            }
+            h_abs *= fmax(0.2, 0.9 * bdf_pow(error_norm, -0.2));
+            rejected = true;
+        }
+        t = t_new;
+        BDF_UNROLL for (int i = 0; i < NX; ++i) y[i] = yn[i];
+        if (act) { BDF_UNROLL for (int i = 0; i < NX; ++i) K_(0, i) = K_(6, i); }
+        BDF_SYNC();
+    }
+#undef K_
+    return 0;
+}
+
+CPDP_GLOBAL void __launch_bounds__(BDF_THREADS, CPDP_BDF_MINB) k_riccati_rk45(AuxArgs a) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (a.solve_status && (a.solve_status[b] == ST_NUMERIC || a.solve_status[b] == ST_RUNNING)) {
+        if (lane == 0) a.aux_status[b] = 3;
+        return;
+    }
+    BDF_SM();
+    const bool act = lane < NC, isP = lane < NX;
+    const int lc = act ? lane : 0;
+    CPDP_LOOP for (int q = lane; q < MSZ; q += BDF_THREADS) sm[bo::M + q] = 0.0;        // structural zeros of the PMP matrices
+    const int N = a.N;
+    AuxProblem p;
+    p.X = a.X + (size_t)b * (N + 1) * NX; p.U = a.U + (size_t)b * (N + 1) * NU; p.Lam = a.Lam + (size_t)b * (N + 1) * NX;
+    p.th = a.theta + (size_t)b * a.theta_stride; p.pd = a.pdata + (size_t)b * NQ; p.PW = nullptr; p.dt = a.T / N; p.N = N;
+    double* PW = a.PW + (size_t)b * (N + 1) * NYR;
+    double* s_hxx = sm + bo::PV; double* s_hxe = sm + bo::XA;     // terminal condition (CPDP.py:327-331) staged in scratch
+    if (lane == 0) {
+        const double tN = p.dt * N;
+        double xT[NX];
+        const int lo = interp_lo(tN, p.dt, N);
+        CPDP_LOOP for (int i = 0; i < NX; ++i) xT[i] = interp_val(p.X[(size_t)lo * NX + i], p.X[(size_t)(lo + 1) * NX + i], p.dt * lo, p.dt * (lo + 1), tN);
+        PdBuf pdb;
+        Model::term2(xT, p.th, pd_at(p.pd, tN, pdb), s_hxx, s_hxe);
+    }
+    BDF_SYNC();
+    double y[NX];
+    BDF_UNROLL for (int i = 0; i < NX; ++i) y[i] = isP ? 0.5 * (s_hxx[i * NX + lc] + s_hxx[lc * NX + i]) : s_hxe[i * NP + (act ? lc - NX : 0)];
+    BDF_SYNC();
+    int nrhs = 0, nsteps = 0, st = 0;
+    CPDP_LOOP for (int k = N; k >= 0; --k) {
+        if (act) {                                                  // packed node table [upper-tri(P) | W] for the forward sweep
+            BDF_UNROLL for (int i = 0; i < NX; ++i) {
+                if (isP) { if (i <= lc) PW[(size_t)k * NYR + tri(i, lc)] = y[i]; }
+                else PW[(size_t)k * NYR + NT + i * NP + (lc - NX)] = y[i];
+            }
+        }
+        if (k == 0) break;
+        st = rkw_interval(sm, p, p.dt * k, p.dt * (k - 1), a.rtol_b, a.atol_b, y, nrhs, nsteps);
+        BDF_SYNC();
+        if (st != 0) break;
+    }
+    if (lane == 0) { a.aux_status[b] = st; a.counters[b * NCOUNTERS + 0] = nrhs; a.counters[b * NCOUNTERS + 1] = nsteps; }
+}
+
 }  // namespace CPDP_NS
