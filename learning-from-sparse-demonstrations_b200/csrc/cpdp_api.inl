@@ -30,8 +30,9 @@ static WsLayout ws_carve(char* base, int B, int N, int S) {
     auto takeI = [&](size_t n) { int* p = base ? (int*)(base + off) : nullptr; off = al(off + n * sizeof(int)); return p; };
     const size_t BN = (size_t)B * N, BN1 = (size_t)B * (N + 1);
     SolveArgs& a = w.sa;
-    a.xs = takeD(BN * 4 * S * NX);
-    a.mu = takeD(BN * 4 * S * NX);
+    const size_t BNT = (BN + STAGE_TILE - 1) / STAGE_TILE * STAGE_TILE;     // stage arrays are tiled by STAGE_TILE intervals
+    a.xs = takeD(BNT * 4 * S * NX);
+    a.mu = takeD(BNT * 4 * S * NX);
     a.AB = takeD(BN * NX * NZ);
     a.H = takeD(BN * NZ * NZ);
     a.gL = takeD(BN * NZ);

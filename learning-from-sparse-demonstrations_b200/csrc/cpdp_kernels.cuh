@@ -112,6 +112,15 @@ CPDP_HD void rk4_interval(const double* x, const double* u, const double* th, co
     for (int i = 0; i < NX; ++i) xe[i] = xa[i];
 }
 
+// Layout of the stage states / stage adjoints handed from k_stage_adjoint to k_stage_hessian: tiles of STAGE_TILE intervals,
+// element (stage row, e) of the tile's intervals contiguous -- [tile][row][e][interval in tile].  k_stage_adjoint runs one thread
+// per interval, so a warp's store of one element is 256 contiguous bytes (the plain [interval][row][e] layout made it 32 separate
+// sectors per store instruction: the kernel sat on a full load/store queue, lg_throttle 22 per issued instruction).
+constexpr int STAGE_TILE = 32;
+CPDP_HD size_t stage_off(int idx, int row, int nrows, int e) {
+    return (((size_t)(idx / STAGE_TILE) * nrows + row) * NX + e) * STAGE_TILE + (idx % STAGE_TILE);
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_stage_adjoint: one thread per (problem, interval).
 // Forward RK4 rollout storing the 4S stage states, defect and cost; then the discrete adjoint of the interval map
@@ -141,23 +150,24 @@ CPDP_D void stage_adjoint_item(const SolveArgs& a, int b, int k) {
         for (int i = 0; i < NX; ++i) x[i] = xk[i];
         for (int i = 0; i < NU; ++i) u[i] = uk[i];
     }
-    double* xs = a.xs + (size_t)idx * 4 * a.S * NX;
-    double* mus = a.mu + (size_t)idx * 4 * a.S * NX;
+    const int nrows = 4 * a.S;
+    double* xs = a.xs + stage_off(idx, 0, nrows, 0);           // element (row, e) of this interval: xs[(row * NX + e) * STAGE_TILE]
+    double* mus = a.mu + stage_off(idx, 0, nrows, 0);
     double q = 0.0;
     {   // forward
         double kk[NX], xt[NX], xn[NX], c;
         for (int s = 0; s < a.S; ++s) {
-            double* st = xs + (size_t)s * 4 * NX;
-            for (int i = 0; i < NX; ++i) st[i] = x[i];
+            double* st = xs + (size_t)s * 4 * NX * STAGE_TILE;
+            for (int i = 0; i < NX; ++i) st[i * STAGE_TILE] = x[i];
             Model::fc(x, u, th, pd, kk, c);
             double qa = c;
-            for (int i = 0; i < NX; ++i) { xn[i] = x[i] + DT / 6 * kk[i]; xt[i] = x[i] + DT / 2 * kk[i]; st[NX + i] = xt[i]; }
+            for (int i = 0; i < NX; ++i) { xn[i] = x[i] + DT / 6 * kk[i]; xt[i] = x[i] + DT / 2 * kk[i]; st[(NX + i) * STAGE_TILE] = xt[i]; }
             Model::fc(xt, u, th, pd, kk, c);
             qa += 2 * c;
-            for (int i = 0; i < NX; ++i) { xn[i] += DT / 3 * kk[i]; xt[i] = x[i] + DT / 2 * kk[i]; st[2 * NX + i] = xt[i]; }
+            for (int i = 0; i < NX; ++i) { xn[i] += DT / 3 * kk[i]; xt[i] = x[i] + DT / 2 * kk[i]; st[(2 * NX + i) * STAGE_TILE] = xt[i]; }
             Model::fc(xt, u, th, pd, kk, c);
             qa += 2 * c;
-            for (int i = 0; i < NX; ++i) { xn[i] += DT / 3 * kk[i]; xt[i] = x[i] + DT * kk[i]; st[3 * NX + i] = xt[i]; }
+            for (int i = 0; i < NX; ++i) { xn[i] += DT / 3 * kk[i]; xt[i] = x[i] + DT * kk[i]; st[(3 * NX + i) * STAGE_TILE] = xt[i]; }
             Model::fc(xt, u, th, pd, kk, c);
             qa += c;
             for (int i = 0; i < NX; ++i) x[i] = xn[i] + DT / 6 * kk[i];
@@ -183,12 +193,12 @@ CPDP_D void stage_adjoint_item(const SolveArgs& a, int b, int k) {
         double ax[NX], xi[NX], kap[NX], g_u[NU], xst[NX];
         for (int i = 0; i < NX; ++i) { ax[i] = 0.0; xi[i] = 0.0; }
         for (int st = 3; st >= 0; --st) {
-            const double* xsp = xs + ((size_t)s * 4 + st) * NX;
-            for (int i = 0; i < NX; ++i) xst[i] = xsp[i];
+            const double* xsp = xs + ((size_t)s * 4 + st) * NX * STAGE_TILE;
+            for (int i = 0; i < NX; ++i) xst[i] = xsp[i * STAGE_TILE];
             const double cnext = (st < 3) ? aco[st + 1] * DT : 0.0;
             for (int i = 0; i < NX; ++i) kap[i] = bco[st] * DT * adj[i] + cnext * xi[i];
-            double* mp = mus + ((size_t)s * 4 + st) * NX;
-            for (int i = 0; i < NX; ++i) mp[i] = kap[i];
+            double* mp = mus + ((size_t)s * 4 + st) * NX * STAGE_TILE;
+            for (int i = 0; i < NX; ++i) mp[i * STAGE_TILE] = kap[i];
             Model::hgrad(xst, u, th, pd, kap, bco[st] * DT, xi, g_u);
             for (int i = 0; i < NX; ++i) ax[i] += xi[i];
             for (int i = 0; i < NU; ++i) gu[i] += g_u[i];
@@ -290,8 +300,7 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
                 const int q = t / (2 * NX), e = t % (2 * NX);                                                   \
                 const int g2 = s_gi[q];                                                                         \
                 if (g2 >= 0) {                                                                                  \
-                    const size_t base = ((size_t)g2 * nstage + (size_t)(sidx)) * NX;                            \
-                    pre[p_] = (e < NX) ? a.xs[base + e] : a.mu[base + e - NX];                                  \
+                    pre[p_] = (e < NX) ? a.xs[stage_off(g2, (sidx), nstage, e)] : a.mu[stage_off(g2, (sidx), nstage, e - NX)];  \
                 }                                                                                               \
             }                                                                                                   \
         }
