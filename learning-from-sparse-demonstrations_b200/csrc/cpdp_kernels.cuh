@@ -238,7 +238,9 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
     CPDP_SHARED double s_th[KPC][NP];
     CPDP_SHARED double s_pd[KPC][NQT > 0 ? NQT : 1];
     constexpr int SXS = (NX + 1) & ~1;                 // even row length: the Hessian accumulation reads the rows with 128-bit loads
-    CPDP_SHARED __align__(16) double s_S[KPC][NZ][SXS];
+    // rows 0 .. NZ-1 = the NZ sensitivity columns; rows NZ .. NZ+HW-2 repeat rows 0 .. HW-2, so that thread j reads rows j .. j+HW-1
+    // without wrapping: consecutive lanes then read consecutive rows (7 x 16 bytes apart: a quarter-warp covers all banks)
+    CPDP_SHARED __align__(16) double s_S[KPC][NZ + NZ / 2][SXS];
     CPDP_SHARED double s_hzu[KPC][NZ][NU];     // control rows of each thread's Hessian-vector product (dynamic index in the accumulation)
     CPDP_SHARED int s_gi[KPC];                 // global interval index b*N+k of each slot, -1 if none
     constexpr int HW = NZ / 2 + 1;
@@ -280,7 +282,7 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
         int rowu[HW];                              // i - NX for the control rows, -1 for the state rows
         for (int w = 0; w < HW; ++w) {
             const int i = (j + w) % NZ;
-            rowp[w] = s_S[kk < KPC ? kk : 0][i];
+            rowp[w] = s_S[kk < KPC ? kk : 0][j + w];
             rowu[w] = i >= NX ? i - NX : -1;
             Hc[w] = 0.0;
         }
@@ -297,7 +299,7 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
             const int t = tid + p_ * HESS_THREADS;                                                              \
             pre[p_] = 0.0;                                                                                      \
             if (t < KPC * 2 * NX) {                                                                             \
-                const int q = t / (2 * NX), e = t % (2 * NX);                                                   \
+                const int q = t % KPC, e = t / KPC;     /* intervals fastest: neighbours share sectors of the tiled arrays */  \
                 const int g2 = s_gi[q];                                                                         \
                 if (g2 >= 0) {                                                                                  \
                     pre[p_] = (e < NX) ? a.xs[stage_off(g2, (sidx), nstage, e)] : a.mu[stage_off(g2, (sidx), nstage, e - NX)];  \
@@ -308,7 +310,7 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
         for (int p_ = 0; p_ < NPRE; ++p_) {                                                                     \
             const int t = tid + p_ * HESS_THREADS;                                                              \
             if (t < KPC * 2 * NX) {                                                                             \
-                const int q = t / (2 * NX), e = t % (2 * NX);                                                   \
+                const int q = t % KPC, e = t / KPC;     /* intervals fastest: neighbours share sectors of the tiled arrays */  \
                 if (e < NX) s_x[buf][q][e] = pre[p_]; else s_mu[buf][q][e - NX] = pre[p_];                      \
             }                                                                                                   \
         }
@@ -325,6 +327,7 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
                     for (int i = 0; i < NX; ++i) dX[i] = Sx[i] + ca * df[i];
                     Model::dir(s_x[cur][kk], s_u[kk], s_th[kk], s_pd[kk], s_mu[cur][kk], bco[st] * DT, dX, du, df, hz);
                     for (int i = 0; i < NX; ++i) s_S[kk][j][i] = dX[i];
+                    if (j < NZ / 2) { for (int i = 0; i < NX; ++i) s_S[kk][NZ + j][i] = dX[i]; }
                     for (int i = 0; i < NU; ++i) s_hzu[kk][j][i] = hz[NX + i];      // (read back by this thread only)
                 }
                 __syncthreads();
@@ -343,9 +346,9 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
 #pragma unroll
                         for (int w = 0; w < HW; ++w) { acc[w] += c2[w].x * hz[e]; acc[w] += c2[w].y * hz[e + 1]; }
                     }
-                    if (NX & 1) {
+                    if (NX & 1) {                                          // (last element through a 128-bit load as well: the 64-bit form conflicts two-way)
 #pragma unroll
-                        for (int w = 0; w < HW; ++w) acc[w] += rowp[w][NX - 1] * hz[NX - 1];
+                        for (int w = 0; w < HW; ++w) acc[w] += reinterpret_cast<const double2*>(rowp[w] + NX - 1)->x * hz[NX - 1];
                     }
 #else
                     for (int w = 0; w < HW; ++w) { for (int e = 0; e < NX; ++e) acc[w] += rowp[w][e] * hz[e]; }
