@@ -276,7 +276,7 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
         const int gi = mine ? s_gi[kk] : -1;
 
         // The Hessian is symmetric: thread j accumulates the HW entries (i, j), i = (j + w) mod NZ, w < HW, and mirrors them at
-        // the end -- every unordered pair {i, j} is covered once (for even NZ the pairs at distance NZ/2 twice: not mirrored).
+        // the end -- every unordered pair {i, j} is covered once (for even NZ the pairs at distance NZ/2 twice: the lower thread writes them).
         double Sx[NX], Sn[NX], dX[NX], df[NX], du[NU], hz[NZ], Hc[HW];
         const double* rowp[HW];                    // row i of this interval's stage sensitivities
         int rowu[HW];                              // i - NX for the control rows, -1 for the state rows
@@ -370,8 +370,10 @@ CPDP_GLOBAL void __launch_bounds__(HESS_THREADS, CPDP_HESS_MINB) k_stage_hessian
             double* H = a.H + (size_t)gi * NZ * NZ;
             for (int w = 0; w < HW; ++w) {
                 const int i = (j + w) % NZ;
+                // (even NZ: the pairs at distance NZ/2 are computed by both of their threads; the lower one writes them)
+                if ((NZ % 2 == 0) && w == NZ / 2 && j >= NZ / 2) continue;
                 H[i * NZ + j] = Hc[w];
-                if (w != 0 && !(NZ % 2 == 0 && w == NZ / 2)) H[j * NZ + i] = Hc[w];
+                if (w != 0) H[j * NZ + i] = Hc[w];                     // exactly symmetric: k_newton_step reads one triangle's worth
             }
         }
     }
@@ -582,7 +584,7 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
             //  chain of short dependent phases, an L2 round trip inside any of them is paid 50 times per problem and round)
             double ab[NX], hq[NZ];
             NWT_UNROLL for (int e2 = 0; e2 < NX; ++e2) ab[e2] = isZ ? ABg[e2 * NZ + jz] : 0.0;
-            NWT_UNROLL for (int r_ = 0; r_ < NZ; ++r_) hq[r_] = isZ ? 0.5 * (Hg[r_ * NZ + jz] + Hg[jz * NZ + r_]) : 0.0;
+            NWT_UNROLL for (int r_ = 0; r_ < NZ; ++r_) hq[r_] = isZ ? Hg[r_ * NZ + jz] : 0.0;     // (k_stage_hessian writes H exactly symmetric: 0.5 (H + H') = H)
             const double gl = isZ ? gLg[jz] : 0.0;
             if (isX) { s_dk[jx] = dk1[jx]; s_lk[jx] = lk1[jx]; }
             NWT_UNROLL for (int e2 = 0; e2 < NX; ++e2) if (isZ) s_AB[e2 * NZS + jz] = ab[e2];

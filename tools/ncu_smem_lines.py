@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Developer tool: shared-memory wavefronts per source line of one kernel in an .ncu-rep (--set full, --import-source on):
-actual vs ideal wavefronts, i.e. where the bank conflicts are.  usage: ncu_smem_lines.py report.ncu-rep kernel-substring [top]"""
+actual vs ideal wavefronts, i.e. where the bank conflicts are.  usage: ncu_smem_lines.py report.ncu-rep kernel-substring [top] [--global]   (--global: rank the lines by global-memory sectors)"""
 import collections
 import os
 import sys
@@ -10,7 +10,7 @@ import ncu_report  # noqa: E402
 
 rep = ncu_report.load_report(sys.argv[1])
 pat = sys.argv[2]
-top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+top = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 25
 rng = rep.range_by_idx(0)
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for ai in range(rng.num_actions()):
@@ -33,7 +33,8 @@ for ai in range(rng.num_actions()):
     toti = sum(v["memory_l1_wavefronts_shared_ideal"] for v in by.values())
     print("kernel %s: shared wavefronts %.3e (ideal %.3e)" % (act.name(), tot, toti))
     srcs = {}
-    for (fn, ln), v in sorted(by.items(), key=lambda kv: -kv[1]["memory_l1_wavefronts_shared"])[:top]:
+    order = "memory_l2_theoretical_sectors_global" if "--global" in sys.argv else "memory_l1_wavefronts_shared"
+    for (fn, ln), v in sorted(by.items(), key=lambda kv: -kv[1][order])[:top]:
         if fn not in srcs:
             cand = [os.path.join(dp, fn) for dp, _, fs in os.walk(root) if fn in fs]
             srcs[fn] = open(cand[0]).read().split("\n") if cand else []
