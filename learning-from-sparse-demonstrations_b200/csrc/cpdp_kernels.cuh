@@ -688,7 +688,7 @@ CPDP_D void newton_step_problem(const SolveArgs& a, const int b) {
         // rows of K, V, [A B] for this lane: one batch of independent loads
         double kr[NX], vr[NX], ar[NZ];
         const int lu = (lane < NU) ? lane : 0;
-        NWT_UNROLL for (int c = 0; c < NX; ++c) { kr[c] = Kk[lu * NX + c]; vr[c] = Vs[(size_t)k * NX * NX + jx * NX + c]; }
+        NWT_UNROLL for (int c = 0; c < NX; ++c) { kr[c] = Kk[lu * NX + c]; vr[c] = Vs[(size_t)k * NX * NX + c * NX + jx]; }   // (V is exactly symmetric: column jx = row jx, read coalesced)
         NWT_UNROLL for (int c = 0; c < NZ; ++c) ar[c] = ABg[jx * NZ + c];
         const double kf0 = kfk[lu], vs0 = vs[(size_t)k * NX + jx], df0 = dfc[(size_t)(k + 1) * NX + jx];
         if (lane < NU) {
