@@ -102,7 +102,7 @@ def test_device_learner_matches_host_learner(method):
     oc.aux_mode = oc.MODE_RK45
     x0 = np.zeros((2, 2))
     taus, wp, sel = np.array([0.3, 0.8]), np.array([[[1.4], [2.9]], [[1.5], [2.7]]]), [0]
-    para = {"learning_rate": 0.02, "iter_num": 3, "method": method.replace("True", ""), "mu": 0.9,
+    para = {"learning_rate": 0.02, "iter_num": 2, "method": method.replace("True", ""), "mu": 0.9,
             "true_loss_print_flag": method.endswith("True"), "beta_1": 0.9, "beta_2": 0.999, "epsilon": 1e-8}
     H = Learner(cpdp_grad_fn(oc, x0, 1.0, taus, wp, sel), 3)
     H.load_optimization_function(para)
@@ -110,7 +110,7 @@ def test_device_learner_matches_host_learner(method):
     D = DeviceLearner(oc, x0, 1.0, taus, wp, sel)
     D.load_optimization_function(para)
     th_d = D.run([1.0, 0.5, 1.5])
-    assert len(D.loss_trace) == len(H.loss_trace) == 3, (D.loss_trace, H.loss_trace)
+    assert len(D.loss_trace) == len(H.loss_trace) == 2, (D.loss_trace, H.loss_trace)
     assert np.array_equal(np.array(D.parameter_trace), np.array(H.parameter_trace)), method
     assert np.array_equal(np.array(D.loss_trace), np.array(H.loss_trace))
     assert np.array_equal(th_d, th_h)
