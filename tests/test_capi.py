@@ -40,7 +40,8 @@ def test_library_exports(model, dims):
 
 
 def test_sass_is_sm100a_fp64():
-    """The quadrotor library holds sm_100 SASS with DFMA instructions and no tensor-core (HMMA/UTC*MMA) code."""
+    """The quadrotor library holds sm_100 SASS with DFMA instructions, bulk-copy (TMA) + mbarrier instructions and no tensor-core
+    (HMMA/UTC*MMA) code."""
     import shutil
     import subprocess
     so = os.path.join(_capi.LIB_DIR, "libcpdp_quadrotor.so")
@@ -51,3 +52,5 @@ def test_sass_is_sm100a_fp64():
     assert "sm_100" in out
     assert "DFMA" in out
     assert "HMMA" not in out and "UTCHMMA" not in out
+    # the forward sweep's node-row ring is fed by the TMA engine: bulk copy global -> shared, completion on an mbarrier
+    assert "UBLKCP" in out and "SYNCS.PHASECHK" in out and "SYNCS.ARRIVE.TRANS64" in out
